@@ -1,0 +1,176 @@
+"""Generate tests/golden/*.npz from the UNMODIFIED reference.  TEST INFRASTRUCTURE ONLY.
+
+Run in the build container (needs /root/reference):   python oracle/make_golden.py
+The reference has no golden vectors of its own, so these fixtures — outputs of
+the reference's own functions at fixed seeds — are what pins the oracle (and through it the
+CUDA engine).  Nets are NOT stored (110 MB): they are rebuilt from the seed by
+oracle.mofa_oracle.build_nets(); this script asserts that rebuild is bit-identical to the
+reference's own construction.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from oracle import mofa_oracle as O  # noqa: E402
+from oracle import ref_loader  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def _latents(seed):
+    """Latents drawn from the reference's priors (configs/texShpDistribution.npy, consumed by
+    tools/wild_fit_base.py:21-45); expression code ~ U[0,1) as render_class.py:53-56."""
+    d = np.load(os.path.join(ref_loader.REF_ROOT, "configs", "texShpDistribution.npy"), allow_pickle=True).item()
+    g = torch.Generator().manual_seed(seed)
+    f = lambda k: torch.as_tensor(np.asarray(d[k]), dtype=torch.float32)
+    shape = f("shape_mean").reshape(1, 50) + f("shape_std").reshape(1, 50) * torch.randn(1, 50, generator=g)
+    tex = f("texture_mean").reshape(256) + f("texture_std").reshape(256) * torch.randn(256, generator=g)
+    exp = torch.rand(1, 30, generator=g)
+    return shape, tex, exp
+
+
+def _check_same_nets(ref_net, ora_net):
+    a, b = ref_net.state_dict(), ora_net.state_dict()
+    assert list(a.keys()) == list(b.keys()), "state_dict key order differs"
+    for k in a:
+        assert torch.equal(a[k], b[k]), f"init differs at {k}"
+
+
+def _camera(H, W, angle):
+    focal = 1200.0 * H / 512.0
+    K = np.array([[focal, 0, 0.5 * W], [0, focal, 0.5 * H], [0, 0, 1]], np.float64)
+    c2w = O.pose_spherical(float(angle), 0.0, 16.0)
+    return K, c2w
+
+
+def render_case(name, seed, W_c, D_c, W_f, D_f, H, W, angle, N_samples, N_importance, crop=None,
+                perturb=0.0, raw_noise_std=0.0, pytest=False, white_bkgd=False, sigma_bias=None,
+                lindisp=False):
+    ref = ref_loader.load()
+    coarse, fine, renderer = ref_loader.build_reference(seed, W_c, D_c, W_f, D_f)
+    oc, of, ostyle = O.build_nets(seed, W_c, D_c, W_f, D_f)
+    _check_same_nets(coarse, oc)
+    if fine is not None:
+        _check_same_nets(fine, of)
+    _check_same_nets(renderer.idSpecificMod, ostyle)
+    if sigma_bias is not None:
+        for n in (coarse, fine):
+            if n is not None:
+                n.alpha_linear[0].bias.data.fill_(sigma_bias)
+    shape, tex, exp = _latents(seed + 100)
+    K, c2w = _camera(H, W, angle)
+    rays_o, rays_d = ref.helpers.get_rays(H, W, K, c2w[:3, :4])
+    rays_o = rays_o.reshape(-1, 3)
+    rays_d = rays_d.reshape(-1, 3)
+    if crop is not None:  # deterministic subset of rays (keeps fixtures and CPU time small)
+        idx = torch.linspace(0, H * W - 1, crop).long()
+        rays_o, rays_d = rays_o[idx], rays_d[idx]
+    kwargs = dict(network_fn=coarse, network_fine=fine, N_samples=N_samples, N_importance=N_importance,
+                  perturb=perturb, raw_noise_std=raw_noise_std, white_bkgd=white_bkgd, lindisp=lindisp,
+                  use_viewdirs=True, ndc=False, near=8.0, far=26.0, pytest=pytest, retraw=True)
+    with torch.no_grad():
+        rgb, disp, acc, extras = renderer.render_fitting(H, W, K, chunk=4096, rays=(rays_o, rays_d),
+                                                         shapeCodes=shape, uvCodes=tex, expType=20,
+                                                         expCodes=exp, **kwargs)
+    out = dict(rgb_map=rgb, disp_map=disp, acc_map=acc)
+    for k in ("rgb0", "disp0", "acc0", "z_std", "raw"):
+        if k in extras:
+            out[k] = extras[k]
+    meta = dict(seed=seed, W_c=W_c, D_c=D_c, W_f=W_f, D_f=D_f, H=H, W=W, N_samples=N_samples,
+                N_importance=N_importance, perturb=perturb, raw_noise_std=raw_noise_std,
+                pytest=int(pytest), white_bkgd=int(white_bkgd), lindisp=int(lindisp),
+                sigma_bias=(np.nan if sigma_bias is None else sigma_bias), near=8.0, far=26.0)
+    arrays = {f"out_{k}": v.detach().numpy().astype(np.float32) for k, v in out.items()}
+    arrays.update(rays_o=rays_o.numpy(), rays_d=rays_d.numpy(), shape=shape.numpy(), tex=tex.numpy(),
+                  exp=exp.numpy(), K=K, c2w=c2w.numpy())
+    for k, v in meta.items():
+        arrays[f"meta_{k}"] = np.asarray(v)
+    if "out_raw" in arrays and arrays["out_raw"].size > 200_000:
+        del arrays["out_raw"]
+    os.makedirs(OUT, exist_ok=True)
+    np.savez_compressed(os.path.join(OUT, f"{name}.npz"), **arrays)
+    nan = int(np.isnan(arrays["out_disp_map"]).sum())
+    print(f"[golden] {name}: rays={rays_o.shape[0]} rgb mean={arrays['out_rgb_map'].mean():.4f} "
+          f"acc mean={arrays['out_acc_map'].mean():.4f} disp NaNs={nan}")
+
+
+def op_cases():
+    """Op-level known answers from the reference's own functions."""
+    ref = ref_loader.load()
+    g = torch.Generator().manual_seed(7)
+    arrays = {}
+    # positional encoding (models/model.py:15-63)
+    x = (torch.rand(64, 3, generator=g) * 2 - 1) * 20.0
+    e10, _ = ref.model.get_embedder(10, 0)
+    e4, _ = ref.model.get_embedder(4, 0)
+    arrays.update(pe_x=x.numpy(), pe_out10=e10(x).numpy(), pe_out4=e4(x).numpy())
+    # raw2outputs (render_class.py:440-482): includes zero-density rays (NaN disp) and white bkgd
+    N, S = 48, 64
+    raw = torch.randn(N, S, 4, generator=g) * 2.0
+    raw[:8, :, 3] = -5.0  # relu -> 0 density everywhere: acc == 0, disp = NaN
+    z = torch.sort(torch.rand(N, S, generator=g) * 18 + 8, -1)[0]
+    d = torch.randn(N, 3, generator=g)
+    for wb in (0, 1):
+        o = ref.render_class.raw2outputs(raw, z, d, 0, bool(wb))
+        for nm, v in zip(("rgb", "disp", "acc", "weights", "depth"), o):
+            arrays[f"r2o_wb{wb}_{nm}"] = v.numpy()
+    arrays.update(r2o_raw=raw.numpy(), r2o_z=z.numpy(), r2o_d=d.numpy())
+    # sample_pdf (run_nerf_helpers.py:203-247): det and explicit-u (pytest hook) variants
+    bins = 0.5 * (z[:, 1:] + z[:, :-1])
+    w = o[3][:, 1:-1]
+    arrays["pdf_det"] = ref.helpers.sample_pdf(bins, w, 64, det=True).numpy()
+    arrays["pdf_rand_pytest"] = ref.helpers.sample_pdf(bins, w, 64, det=False, pytest=True).numpy()
+    np.random.seed(0)
+    arrays["pdf_u"] = np.random.rand(N, 64).astype(np.float32)
+    arrays.update(pdf_bins=bins.numpy(), pdf_w=w.numpy())
+    # NeRF.forward (models/model.py:121-137) on a small seeded net
+    torch.manual_seed(3)
+    net = ref.model.NeRF(D=8, W=256, input_ch_shapeCodes=50, input_ch_textureCodes=256, input_ch=93,
+                         output_ch=5, skips=[4], input_ch_views=27, use_viewdirs=True).eval()
+    torch.manual_seed(3)
+    onet = O.NeRF(8, 256, 93, 27, 256, 50).eval()
+    _check_same_nets(net, onet)
+    P = 32
+    a = torch.randn(P, 93, generator=g)
+    b = torch.randn(P, 50, generator=g) * 0.03
+    c = torch.randn(P, 27, generator=g)
+    t = torch.randn(P, 256, generator=g) * 0.3
+    with torch.no_grad():
+        arrays.update(net_in_pts=a.numpy(), net_in_shape=b.numpy(), net_in_views=c.numpy(),
+                      net_in_tex=t.numpy(), net_out=net(a, b, c, t).numpy())
+    # get_rays (run_nerf_helpers.py:153-168)
+    K, c2w = _camera(6, 10, 30.0)
+    ro, rd = ref.helpers.get_rays(6, 10, K, c2w[:3, :4])
+    arrays.update(rays_K=K, rays_c2w=c2w.numpy(), rays_o=ro.numpy(), rays_d=rd.numpy())
+    os.makedirs(OUT, exist_ok=True)
+    np.savez_compressed(os.path.join(OUT, "ops.npz"), **arrays)
+    print("[golden] ops.npz written")
+
+
+def main():
+    torch.set_num_threads(os.cpu_count())
+    op_cases()
+    # config #1 (plumbing): 64x64, 32 samples, coarse only
+    render_case("cfg1_64x64_s32", 0, 256, 8, 1024, 10, 64, 64, 0.0, 32, 0)
+    # small two-pass case with a narrow fine net (fast on CPU)
+    render_case("small_w256", 1, 256, 8, 256, 10, 20, 20, -30.0, 64, 64, crop=160)
+    # the real configuration (coarse 256x8 + fine 1024x10), 64+128 evaluations per ray
+    render_case("full_w1024", 5, 256, 8, 1024, 10, 400, 400, 60.0, 64, 64, crop=48)
+    # pytest-hook mode: seeded stratified jitter, random u, sigma noise
+    render_case("perturb_pytest", 2, 256, 8, 256, 10, 16, 16, 0.0, 64, 64, crop=64, perturb=1.0,
+                raw_noise_std=1.0, pytest=True)
+    # empty space: negative sigma bias => acc ~ 0, NaN disparity; white background; lindisp
+    render_case("empty_white", 4, 256, 8, 256, 10, 16, 16, 20.0, 64, 64, crop=64, white_bkgd=True,
+                sigma_bias=-30.0, lindisp=True)
+
+
+if __name__ == "__main__":
+    main()
