@@ -1,0 +1,668 @@
+// C-ABI implementation (include/mofa_b200.h): context, weight repack, latent fold, the layer program
+// of the two MoFaNeRF MLPs and the render_rays orchestration.
+#include "../../include/mofa_b200.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "engine.h"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return 1;
+}
+
+#define CK(expr)                                                                                   \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess)                                                                         \
+      return fail("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__);     \
+  } while (0)
+
+constexpr int kNShape = 50, kNExp = 30, kNTex = 256, kMultires = 10, kMultiresViews = 4;
+constexpr int kPeXyz = 3 + 6 * kMultires;        // 63
+constexpr int kPeView = 3 + 6 * kMultiresViews;  // 27
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+enum Lat { LAT_NONE = 0, LAT_EXP = 1, LAT_SHAPE = 2, LAT_TEX = 3 };
+enum Src { SRC_X0 = 0, SRC_V = 1, SRC_T0 = 2 };  // SRC_T0 + i = activation buffer i
+
+struct Layer {
+  int N = 0;
+  int nseg = 0;
+  int K[2] = {0, 0};             // padded K per segment
+  __half* w[2] = {nullptr, nullptr};
+  CUtensorMap tmB[2];
+  float* bias_raw = nullptr;     // [N]
+  float* bias_eff = nullptr;     // [N] (== bias_raw when nothing is folded)
+  float* fold_w = nullptr;       // [N, fold_n] fp32 latent columns
+  int fold_n = 0;
+  int fold_lat = LAT_NONE;
+  int BN = 256;
+};
+
+struct Step {
+  int kind;       // 0 dense, 1 alpha head, 2 rgb head
+  int layer;      // index into Net::layers (dense)
+  int in[2];      // Src ids
+  int out;        // Src id (dense)
+};
+
+struct Net {
+  bool loaded = false;
+  int W = 0, D = 0;
+  std::vector<Layer> layers;
+  std::vector<Step> program;
+  float *w_alpha = nullptr, *b_alpha = nullptr, *w_rgb = nullptr, *b_rgb = nullptr;
+  std::vector<void*> allocs;
+};
+
+}  // namespace
+
+struct mofa_b200_ctx {
+  int device = 0;
+  int num_sms = 148;
+  EncodeTiledFn encode = nullptr;
+  Net nets[2];
+  float* lat[4] = {nullptr, nullptr, nullptr, nullptr};  // device copies of the current latents
+  bool latents_set = false;
+  int64_t launches = 0;
+};
+
+namespace {
+
+using namespace mofa;
+
+int make_tmap_2d(mofa_b200_ctx* c, CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t pitch,
+                 uint32_t box_rows) {
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {pitch * sizeof(__half)};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = c->encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail("cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu pitch=%llu box_rows=%u ptr=%p", (int)r,
+                (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)pitch, box_rows, ptr);
+  return 0;
+}
+
+int dev_alloc(Net& n, void** p, size_t bytes) {
+  CK(cudaMalloc(p, bytes));
+  n.allocs.push_back(*p);
+  return 0;
+}
+
+void free_net(Net& n) {
+  for (void* p : n.allocs) cudaFree(p);
+  n = Net();
+}
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// One linear layer of the reference -> engine layer.  Column layout of the reference weight
+// [N, n_lat + K0 (+ K1)] : latent (or PE-extra) columns first except for xyzEncode.Linear0 where the
+// modulated expression code comes *after* the 63 PE columns (render_class.py:83).
+struct LayerSpec {
+  int N;
+  int in_total;       // reference in_features
+  int nseg;
+  int seg_c0[2];      // first column of each activation segment in the reference weight
+  int seg_k[2];       // real width
+  int seg_kpad[2];    // padded to 64
+  int fold_c0, fold_n, fold_lat;
+};
+
+int build_layer(mofa_b200_ctx* c, Net& net, const LayerSpec& sp, const float* w, const float* b, cudaStream_t s) {
+  Layer L;
+  L.N = sp.N;
+  L.nseg = sp.nseg;
+  L.BN = (sp.N % 256 == 0) ? 256 : 128;
+  if (sp.N % L.BN != 0) return fail("layer width %d is not a multiple of 128", sp.N);
+  for (int i = 0; i < sp.nseg; ++i) {
+    L.K[i] = sp.seg_kpad[i];
+    if (dev_alloc(net, reinterpret_cast<void**>(&L.w[i]), sizeof(__half) * (size_t)sp.N * L.K[i])) return 1;
+    CK(launch_pack_weight(w, sp.in_total, sp.seg_c0[i], sp.seg_k[i], L.K[i], sp.N, L.w[i], s));
+    c->launches++;
+    if (make_tmap_2d(c, &L.tmB[i], L.w[i], sp.N, L.K[i], L.K[i], L.BN)) return 1;
+  }
+  if (dev_alloc(net, reinterpret_cast<void**>(&L.bias_raw), sizeof(float) * sp.N)) return 1;
+  CK(cudaMemcpyAsync(L.bias_raw, b, sizeof(float) * sp.N, cudaMemcpyDeviceToDevice, s));
+  L.bias_eff = L.bias_raw;
+  if (sp.fold_n > 0) {
+    L.fold_n = sp.fold_n;
+    L.fold_lat = sp.fold_lat;
+    if (dev_alloc(net, reinterpret_cast<void**>(&L.fold_w), sizeof(float) * (size_t)sp.N * sp.fold_n)) return 1;
+    CK(cudaMemcpy2DAsync(L.fold_w, sizeof(float) * sp.fold_n, w + sp.fold_c0, sizeof(float) * sp.in_total,
+                         sizeof(float) * sp.fold_n, sp.N, cudaMemcpyDeviceToDevice, s));
+    if (dev_alloc(net, reinterpret_cast<void**>(&L.bias_eff), sizeof(float) * sp.N)) return 1;
+  }
+  net.layers.push_back(L);
+  return 0;
+}
+
+int pad64(int k) { return (k + 63) / 64 * 64; }
+
+// Emits dense steps for a run of layers and keeps the 3-buffer allocation invariant:
+// at most {pinned, cur} are live, so one activation buffer is always free.
+struct ProgBuilder {
+  Net& net;
+  int cur = SRC_X0;
+  int pinned = -1;
+  explicit ProgBuilder(Net& n) : net(n) {}
+  int free_buf(int a, int b) const {
+    for (int t = SRC_T0; t < SRC_T0 + 3; ++t)
+      if (t != a && t != b && t != pinned && t != cur) return t;
+    return -1;
+  }
+  void dense(int layer, int in0, int in1) {
+    Step st;
+    st.kind = 0;
+    st.layer = layer;
+    st.in[0] = in0;
+    st.in[1] = in1;
+    st.out = free_buf(in0, in1);
+    net.program.push_back(st);
+    cur = st.out;
+  }
+};
+
+int fold_net(mofa_b200_ctx* c, Net& net, cudaStream_t s) {
+  for (Layer& L : net.layers) {
+    if (L.fold_n == 0) continue;
+    CK(launch_fold_bias(L.fold_w, L.fold_n, 0, L.fold_n, L.bias_raw, c->lat[L.fold_lat], L.N, L.bias_eff, s));
+    c->launches++;
+  }
+  return 0;
+}
+
+struct Workspace {
+  float *z_c, *w_c, *z_f, *raw;
+  __half *X0, *V, *T[3];
+  int64_t P_pad;
+  size_t total;
+};
+
+Workspace carve(void* base, int64_t n_chunk, int S_c, int S_f, int Wmax) {
+  Workspace w;
+  const int S_max = S_f > S_c ? S_f : S_c;
+  w.P_pad = (n_chunk * S_max + 127) / 128 * 128;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off = align_up(off + bytes, 1024);
+    return o;
+  };
+  uint8_t* b = static_cast<uint8_t*>(base);
+  w.z_c = reinterpret_cast<float*>(b + take(sizeof(float) * n_chunk * S_c));
+  w.w_c = reinterpret_cast<float*>(b + take(sizeof(float) * n_chunk * S_c));
+  w.z_f = reinterpret_cast<float*>(b + take(sizeof(float) * n_chunk * (S_f > 0 ? S_f : 1)));
+  w.raw = reinterpret_cast<float*>(b + take(sizeof(float) * 4 * w.P_pad));
+  w.X0 = reinterpret_cast<__half*>(b + take(sizeof(__half) * 64 * w.P_pad));
+  w.V = reinterpret_cast<__half*>(b + take(sizeof(__half) * 64 * w.P_pad));
+  for (int i = 0; i < 3; ++i) w.T[i] = reinterpret_cast<__half*>(b + take(sizeof(__half) * (size_t)Wmax * w.P_pad));
+  w.total = off;
+  return w;
+}
+
+int max_width(mofa_b200_ctx* c) {
+  int w = 0;
+  for (int i = 0; i < 2; ++i)
+    if (c->nets[i].loaded && c->nets[i].W > w) w = c->nets[i].W;
+  return w;
+}
+
+// Runs the MLP program of `net` over the first P_pad rows of the workspace buffers.
+int run_program(mofa_b200_ctx* c, Net& net, const Workspace& ws, int64_t P_rows, uint32_t flags, cudaStream_t s) {
+  const int64_t M = (P_rows + 127) / 128 * 128;
+  auto src_ptr = [&](int id) -> __half* { return id == SRC_X0 ? ws.X0 : id == SRC_V ? ws.V : ws.T[id - SRC_T0]; };
+  for (const Step& st : net.program) {
+    if (st.kind == 0) {
+      const Layer& L = net.layers[st.layer];
+      DenseLaunch d;
+      memset(&d, 0, sizeof(d));
+      for (int i = 0; i < L.nseg; ++i) {
+        d.A[i] = src_ptr(st.in[i]);
+        d.B[i] = L.w[i];
+        d.K[i] = L.K[i];
+        d.lda[i] = L.K[i];   // every source buffer is dense with pitch == its K
+        d.tmB[i] = L.tmB[i];
+      }
+      d.C = src_ptr(st.out);
+      d.ldc = L.N;
+      d.bias = L.bias_eff;
+      d.M = M;
+      d.N = L.N;
+      d.BN = L.BN;
+      d.relu = 1;
+      if (flags & MOFA_FLAG_GEMM_SIMT) {
+        CK(launch_dense_simt(d, s));
+      } else {
+        for (int i = 0; i < L.nseg; ++i)
+          if (make_tmap_2d(c, &d.tmA[i], d.A[i], (uint64_t)M, (uint64_t)L.K[i], (uint64_t)L.K[i], 128)) return 1;
+        if (make_tmap_2d(c, &d.tmC, d.C, (uint64_t)M, (uint64_t)L.N, (uint64_t)L.N, 128)) return 1;
+        CK(launch_dense_tc(d, c->num_sms, s));
+      }
+      c->launches++;
+    } else if (st.kind == 1) {
+      CK(launch_head(src_ptr(st.in[0]), net.W, net.w_alpha, net.b_alpha, 1, ws.raw, 3, P_rows, s));
+      c->launches++;
+    } else {
+      CK(launch_head(src_ptr(st.in[0]), net.W / 2, net.w_rgb, net.b_rgb, 3, ws.raw, 0, P_rows, s));
+      c->launches++;
+    }
+  }
+  return 0;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+int mofa_b200_abi_version(void) { return MOFA_B200_ABI_VERSION; }
+const char* mofa_b200_last_error(void) { return g_err.c_str(); }
+
+int mofa_b200_create(mofa_b200_ctx** out, int device) {
+  if (!out) return fail("mofa_b200_create: out is NULL");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail("mofa_b200_create: no CUDA device (%s); this engine has no CPU path", cudaGetErrorString(e));
+  if (device < 0 || device >= count) return fail("mofa_b200_create: device %d out of range (%d devices)", device, count);
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail("mofa_b200_create: device %d is sm_%d%d; this library contains sm_100a code only", device,
+                prop.major, prop.minor);
+  mofa_b200_ctx* c = new mofa_b200_ctx();
+  c->device = device;
+  c->num_sms = prop.multiProcessorCount;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || fn == nullptr) {
+    delete c;
+    return fail("mofa_b200_create: cuTensorMapEncodeTiled not available from the driver");
+  }
+  c->encode = reinterpret_cast<EncodeTiledFn>(fn);
+  e = mofa::dense_tc_configure();
+  if (e != cudaSuccess) {
+    delete c;
+    return fail("mofa_b200_create: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+  }
+  const int nlat[4] = {1, kNExp, kNShape, kNTex};
+  for (int i = 1; i < 4; ++i) {
+    e = cudaMalloc(reinterpret_cast<void**>(&c->lat[i]), sizeof(float) * nlat[i]);
+    if (e != cudaSuccess) {
+      delete c;
+      return fail("mofa_b200_create: cudaMalloc failed: %s", cudaGetErrorString(e));
+    }
+  }
+  *out = c;
+  return 0;
+}
+
+int mofa_b200_destroy(mofa_b200_ctx* c) {
+  if (!c) return 0;
+  cudaSetDevice(c->device);
+  for (int i = 0; i < 2; ++i) free_net(c->nets[i]);
+  for (int i = 1; i < 4; ++i) cudaFree(c->lat[i]);
+  delete c;
+  return 0;
+}
+
+int64_t mofa_b200_launch_count(mofa_b200_ctx* c) { return c ? c->launches : 0; }
+
+int mofa_b200_load_weights(mofa_b200_ctx* c, int net_id, int W, int D, const float* const* t, int n_tensors,
+                           void* stream) {
+  if (!c) return fail("load_weights: ctx is NULL");
+  if (net_id < 0 || net_id > 1) return fail("load_weights: net must be 0 (coarse) or 1 (fine)");
+  if (W % 256 != 0 || W <= 0) return fail("load_weights: W=%d must be a positive multiple of 256", W);
+  if (D < 6) return fail("load_weights: D=%d must be >= 6 (skipMLP(D, skip=4))", D);
+  const int n2 = D - 5;  // layers in linears2 of each skipMLP: 1 + (D - 6)
+  const int expect = 2 * (4 + 2 * (5 + n2) + 3);
+  if (n_tensors != expect) return fail("load_weights: expected %d tensors for D=%d, got %d", expect, D, n_tensors);
+  CK(cudaSetDevice(c->device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Net& net = c->nets[net_id];
+  free_net(net);
+  net.W = W;
+  net.D = D;
+  int ti = 0;
+  auto next = [&](const float*& w, const float*& b) {
+    w = t[ti++];
+    b = t[ti++];
+  };
+  const float *w, *b;
+  ProgBuilder pb(net);
+  int li = 0;
+  // xyzEncode: skipMLP(D=3, skip=None) -> 4 layers; Linear0 input = [PE(63), exp_mod(30)]
+  for (int i = 0; i < 4; ++i) {
+    next(w, b);
+    LayerSpec sp{};
+    sp.N = W;
+    sp.nseg = 1;
+    if (i == 0) {
+      sp.in_total = kPeXyz + kNExp;
+      sp.seg_c0[0] = 0; sp.seg_k[0] = kPeXyz; sp.seg_kpad[0] = pad64(kPeXyz);
+      sp.fold_c0 = kPeXyz; sp.fold_n = kNExp; sp.fold_lat = LAT_EXP;
+    } else {
+      sp.in_total = W;
+      sp.seg_c0[0] = 0; sp.seg_k[0] = W; sp.seg_kpad[0] = W;
+    }
+    if (build_layer(c, net, sp, w, b, s)) return 1;
+    pb.dense(li++, pb.cur, -1);
+  }
+  // two skipMLP(D, skip=4): latent = shape (linear_BiM_xyz) then texture (linear_uv_xyzBiM)
+  for (int blk = 0; blk < 2; ++blk) {
+    const int nl = blk == 0 ? kNShape : kNTex;
+    const int lat = blk == 0 ? LAT_SHAPE : LAT_TEX;
+    const int x_in = pb.cur;     // xyz_code / sigmaCodes: must survive until linears2.Linear0
+    pb.pinned = x_in;
+    for (int i = 0; i < 5; ++i) {   // linears1.Linear0..4
+      next(w, b);
+      LayerSpec sp{};
+      sp.N = W;
+      sp.nseg = 1;
+      if (i == 0) {
+        sp.in_total = nl + W;
+        sp.seg_c0[0] = nl; sp.seg_k[0] = W; sp.seg_kpad[0] = W;
+        sp.fold_c0 = 0; sp.fold_n = nl; sp.fold_lat = lat;
+      } else {
+        sp.in_total = W;
+        sp.seg_c0[0] = 0; sp.seg_k[0] = W; sp.seg_kpad[0] = W;
+      }
+      if (build_layer(c, net, sp, w, b, s)) return 1;
+      pb.dense(li++, pb.cur, -1);
+    }
+    for (int i = 0; i < n2; ++i) {  // linears2.Linear0..: Linear0 input = cat[x_in(lat, x), h]
+      next(w, b);
+      LayerSpec sp{};
+      sp.N = W;
+      if (i == 0) {
+        sp.nseg = 2;
+        sp.in_total = nl + 2 * W;
+        sp.seg_c0[0] = nl;     sp.seg_k[0] = W; sp.seg_kpad[0] = W;
+        sp.seg_c0[1] = nl + W; sp.seg_k[1] = W; sp.seg_kpad[1] = W;
+        sp.fold_c0 = 0; sp.fold_n = nl; sp.fold_lat = lat;
+        if (build_layer(c, net, sp, w, b, s)) return 1;
+        const int h = pb.cur;
+        pb.dense(li++, x_in, h);
+        pb.pinned = -1;
+      } else {
+        sp.nseg = 1;
+        sp.in_total = W;
+        sp.seg_c0[0] = 0; sp.seg_k[0] = W; sp.seg_kpad[0] = W;
+        if (build_layer(c, net, sp, w, b, s)) return 1;
+        pb.dense(li++, pb.cur, -1);
+      }
+    }
+    if (blk == 0) {   // alpha = alpha_linear(sigmaCodes)   (model.py:130)
+      Step st{1, -1, {pb.cur, -1}, -1};
+      net.program.push_back(st);
+    }
+  }
+  // linear_view_xyBMuv: Linear(27 + W -> W/2) on cat[views, rgbCodes]
+  {
+    next(w, b);
+    LayerSpec sp{};
+    sp.N = W / 2;
+    sp.nseg = 2;
+    sp.in_total = kPeView + W;
+    sp.seg_c0[0] = 0;       sp.seg_k[0] = kPeView; sp.seg_kpad[0] = pad64(kPeView);
+    sp.seg_c0[1] = kPeView; sp.seg_k[1] = W;       sp.seg_kpad[1] = W;
+    if (build_layer(c, net, sp, w, b, s)) return 1;
+    pb.dense(li++, SRC_V, pb.cur);
+  }
+  // alpha_linear (W -> 1), rgb_linear (W/2 -> 3): fp32 copies for the SIMT heads
+  next(w, b);
+  if (dev_alloc(net, reinterpret_cast<void**>(&net.w_alpha), sizeof(float) * W)) return 1;
+  if (dev_alloc(net, reinterpret_cast<void**>(&net.b_alpha), sizeof(float))) return 1;
+  CK(cudaMemcpyAsync(net.w_alpha, w, sizeof(float) * W, cudaMemcpyDeviceToDevice, s));
+  CK(cudaMemcpyAsync(net.b_alpha, b, sizeof(float), cudaMemcpyDeviceToDevice, s));
+  next(w, b);
+  if (dev_alloc(net, reinterpret_cast<void**>(&net.w_rgb), sizeof(float) * 3 * (W / 2))) return 1;
+  if (dev_alloc(net, reinterpret_cast<void**>(&net.b_rgb), sizeof(float) * 3)) return 1;
+  CK(cudaMemcpyAsync(net.w_rgb, w, sizeof(float) * 3 * (W / 2), cudaMemcpyDeviceToDevice, s));
+  CK(cudaMemcpyAsync(net.b_rgb, b, sizeof(float) * 3, cudaMemcpyDeviceToDevice, s));
+  {
+    Step st{2, -1, {pb.cur, -1}, -1};
+    net.program.push_back(st);
+  }
+  net.loaded = true;
+  if (c->latents_set && fold_net(c, net, s)) return 1;
+  return 0;
+}
+
+int mofa_b200_set_latents(mofa_b200_ctx* c, const float* shape50, const float* exp_mod30, const float* tex256,
+                          void* stream) {
+  if (!c) return fail("set_latents: ctx is NULL");
+  if (!shape50 || !exp_mod30 || !tex256) return fail("set_latents: NULL latent pointer");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CK(cudaMemcpyAsync(c->lat[LAT_EXP], exp_mod30, sizeof(float) * kNExp, cudaMemcpyDeviceToDevice, s));
+  CK(cudaMemcpyAsync(c->lat[LAT_SHAPE], shape50, sizeof(float) * kNShape, cudaMemcpyDeviceToDevice, s));
+  CK(cudaMemcpyAsync(c->lat[LAT_TEX], tex256, sizeof(float) * kNTex, cudaMemcpyDeviceToDevice, s));
+  c->latents_set = true;
+  for (int i = 0; i < 2; ++i)
+    if (c->nets[i].loaded && fold_net(c, c->nets[i], s)) return 1;
+  return 0;
+}
+
+static int effective_chunk(int64_t n_rays, int chunk_rays) {
+  int64_t ch = chunk_rays > 0 ? chunk_rays : 2048;
+  if (ch > n_rays) ch = n_rays;
+  if (ch < 1) ch = 1;
+  return static_cast<int>(ch);
+}
+
+size_t mofa_b200_workspace_bytes(mofa_b200_ctx* c, int64_t n_rays, int n_samples, int n_importance, int chunk_rays) {
+  if (!c) return 0;
+  const int ch = effective_chunk(n_rays, chunk_rays);
+  const int S_f = n_importance > 0 ? n_samples + n_importance : 0;
+  int Wmax = max_width(c);
+  if (Wmax == 0) Wmax = 1024;
+  return carve(nullptr, ch, n_samples, S_f, Wmax).total + 1024;
+}
+
+int mofa_b200_render_rays_fwd(mofa_b200_ctx* c, const mofa_b200_render_args* a, void* stream) {
+  if (!c || !a) return fail("render_rays_fwd: NULL argument");
+  if (a->struct_size != sizeof(mofa_b200_render_args))
+    return fail("render_rays_fwd: struct_size %u != %zu (ABI mismatch)", a->struct_size, sizeof(mofa_b200_render_args));
+  if (a->n_rays < 0) return fail("render_rays_fwd: n_rays < 0");
+  if (a->n_rays == 0) return 0;
+  if (!a->rays || a->ray_stride < 11) return fail("render_rays_fwd: rays NULL or ray_stride < 11");
+  const int S_c = a->n_samples, N_i = a->n_importance;
+  const bool fine = (N_i > 0) && a->run_fine;
+  const int S_f = fine ? S_c + N_i : 0;
+  if (S_c < 1 || S_c > 256) return fail("render_rays_fwd: n_samples=%d out of range [1,256]", S_c);
+  if (fine && (S_c < 3 || S_f > 256)) return fail("render_rays_fwd: n_samples+n_importance=%d out of range", S_f);
+  Net& nc = c->nets[MOFA_NET_COARSE];
+  if (!nc.loaded) return fail("render_rays_fwd: coarse network not loaded");
+  if (a->fine_net < 0 || a->fine_net > 1) return fail("render_rays_fwd: fine_net must be 0 or 1");
+  Net& nf = c->nets[a->fine_net];
+  if (fine && !nf.loaded) return fail("render_rays_fwd: fine network (net %d) not loaded", a->fine_net);
+  if (!c->latents_set) return fail("render_rays_fwd: mofa_b200_set_latents has not been called");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+
+  const int ch = effective_chunk(a->n_rays, a->chunk_rays);
+  const int Wmax = max_width(c);
+  if (!a->workspace) return fail("render_rays_fwd: workspace is NULL");
+  uint8_t* wbase = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<size_t>(a->workspace), 1024));
+  const size_t slack = wbase - static_cast<uint8_t*>(a->workspace);
+  Workspace ws = carve(wbase, ch, S_c, S_f, Wmax);
+  if (ws.total + slack > a->workspace_bytes)
+    return fail("render_rays_fwd: workspace too small (%zu < %zu)", a->workspace_bytes, ws.total + slack);
+  const int lindisp = (a->flags & MOFA_FLAG_LINDISP) ? 1 : 0;
+  const int white = (a->flags & MOFA_FLAG_WHITE_BKGD) ? 1 : 0;
+  const int S_last = fine ? S_f : S_c;
+
+  for (int64_t r0 = 0; r0 < a->n_rays; r0 += ch) {
+    const int64_t n = (a->n_rays - r0 < ch) ? (a->n_rays - r0) : ch;
+    const float* rays = a->rays + r0 * a->ray_stride;
+    auto off = [&](float* p, int64_t per_ray) -> float* { return p ? p + r0 * per_ray : nullptr; };
+    auto coff = [&](const float* p, int64_t per_ray) -> const float* { return p ? p + r0 * per_ray : nullptr; };
+
+    // ---- coarse pass
+    CK(launch_zvals_coarse(rays, a->ray_stride, n, S_c, lindisp, a->perturb, coff(a->t_rand, S_c), a->seed, r0,
+                           ws.z_c, s));
+    CK(launch_encode_rays(rays, a->ray_stride, ws.z_c, n, S_c, kMultires, kMultiresViews, ws.X0, ws.V, s));
+    c->launches += 2;
+    if (run_program(c, nc, ws, n * S_c, a->flags, s)) return 1;
+    float* o_rgb = fine ? off(a->rgb0, 3) : off(a->rgb, 3);
+    float* o_disp = fine ? off(a->disp0, 1) : off(a->disp, 1);
+    float* o_acc = fine ? off(a->acc0, 1) : off(a->acc, 1);
+    CK(launch_composite(ws.raw, ws.z_c, rays + 3, a->ray_stride, coff(a->noise_c, S_c), a->raw_noise_std,
+                        a->seed, r0, n, S_c, white, o_rgb, o_disp, o_acc, ws.w_c, nullptr, s));
+    c->launches++;
+    const float* z_last = ws.z_c;
+    if (fine) {
+      // ---- hierarchical resampling + fine pass
+      const int det = (a->perturb == 0.0f) ? 1 : 0;
+      CK(launch_sample_pdf_merge(ws.z_c, ws.w_c, coff(a->u, N_i), det, a->seed, r0, n, S_c, N_i, nullptr, ws.z_f,
+                                 off(a->z_std, 1), s));
+      CK(launch_encode_rays(rays, a->ray_stride, ws.z_f, n, S_f, kMultires, kMultiresViews, ws.X0, ws.V, s));
+      c->launches += 2;
+      if (run_program(c, nf, ws, n * S_f, a->flags, s)) return 1;
+      CK(launch_composite(ws.raw, ws.z_f, rays + 3, a->ray_stride, coff(a->noise_f, S_f), a->raw_noise_std,
+                          a->seed + 0x9E3779B97F4A7C15ull, r0, n, S_f, white, off(a->rgb, 3), off(a->disp, 1),
+                          off(a->acc, 1), a->weights ? off(a->weights, S_f) : nullptr, nullptr, s));
+      c->launches++;
+      z_last = ws.z_f;
+    } else if (a->weights) {
+      CK(launch_copy_f32(ws.w_c, off(a->weights, S_c), n * S_c, s));
+      c->launches++;
+    }
+    if (a->raw) {
+      CK(launch_copy_f32(ws.raw, off(a->raw, (int64_t)S_last * 4), n * S_last * 4, s));
+      c->launches++;
+    }
+    if (a->z_vals) {
+      CK(launch_copy_f32(z_last, off(a->z_vals, S_last), n * S_last, s));
+      c->launches++;
+    }
+  }
+  return 0;
+}
+
+size_t mofa_b200_query_workspace_bytes(mofa_b200_ctx* c, int64_t n_pts) {
+  if (!c) return 0;
+  int Wmax = max_width(c);
+  if (Wmax == 0) Wmax = 1024;
+  return carve(nullptr, n_pts, 1, 0, Wmax).total + 1024;
+}
+
+int mofa_b200_run_network(mofa_b200_ctx* c, int net_id, const float* pts, const float* viewdirs, int64_t n_pts,
+                          float* raw_out, uint32_t flags, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!c) return fail("run_network: ctx is NULL");
+  if (net_id < 0 || net_id > 1 || !c->nets[net_id].loaded) return fail("run_network: net %d not loaded", net_id);
+  if (!c->latents_set) return fail("run_network: mofa_b200_set_latents has not been called");
+  if (n_pts == 0) return 0;
+  if (!pts || !viewdirs || !raw_out || !workspace) return fail("run_network: NULL pointer");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  uint8_t* wbase = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<size_t>(workspace), 1024));
+  const size_t slack = wbase - static_cast<uint8_t*>(workspace);
+  Workspace ws = carve(wbase, n_pts, 1, 0, max_width(c));
+  if (ws.total + slack > workspace_bytes)
+    return fail("run_network: workspace too small (%zu < %zu)", workspace_bytes, ws.total + slack);
+  CK(launch_encode_points(pts, viewdirs, n_pts, kMultires, kMultiresViews, ws.X0, ws.V, s));
+  c->launches++;
+  if (run_program(c, c->nets[net_id], ws, n_pts, flags, s)) return 1;
+  CK(launch_copy_f32(ws.raw, raw_out, n_pts * 4, s));
+  c->launches++;
+  return 0;
+}
+
+int mofa_b200_embed(mofa_b200_ctx* c, const float* x, int64_t n, int multires, float* out, void* stream) {
+  if (!c) return fail("embed: ctx is NULL");
+  if (multires < 0 || multires > 16) return fail("embed: multires out of range");
+  CK(cudaSetDevice(c->device));
+  CK(launch_embed_f32(x, n, multires, out, static_cast<cudaStream_t>(stream)));
+  c->launches++;
+  return 0;
+}
+
+int mofa_b200_raw2outputs(mofa_b200_ctx* c, const float* raw, const float* z, const float* rays_d, int d_stride,
+                          const float* noise, int64_t n, int S, int white_bkgd, float* rgb, float* disp, float* acc,
+                          float* weights, float* depth, void* stream) {
+  if (!c) return fail("raw2outputs: ctx is NULL");
+  if (S < 1 || S > 256) return fail("raw2outputs: S=%d out of range [1,256]", S);
+  CK(cudaSetDevice(c->device));
+  CK(launch_composite(raw, z, rays_d, d_stride, noise, 0.0f, 0, 0, n, S, white_bkgd, rgb, disp, acc, weights, depth,
+                      static_cast<cudaStream_t>(stream)));
+  c->launches++;
+  return 0;
+}
+
+int mofa_b200_sample_pdf_merge(mofa_b200_ctx* c, const float* z, const float* weights, const float* u, int64_t n,
+                               int S, int N_i, float* z_samples, float* z_merged, float* z_std, void* stream) {
+  if (!c) return fail("sample_pdf_merge: ctx is NULL");
+  if (S < 3 || S > 256 || N_i < 1 || S + N_i > 512) return fail("sample_pdf_merge: S=%d N_i=%d out of range", S, N_i);
+  CK(cudaSetDevice(c->device));
+  CK(launch_sample_pdf_merge(z, weights, u, 1, 0, 0, n, S, N_i, z_samples, z_merged, z_std,
+                             static_cast<cudaStream_t>(stream)));
+  c->launches++;
+  return 0;
+}
+
+int mofa_b200_dense(mofa_b200_ctx* c, const void* A0, const void* B0, int K0, const void* A1, const void* B1, int K1,
+                    const float* bias, void* C, int64_t M, int N, int relu, int use_simt, void* stream) {
+  if (!c) return fail("dense: ctx is NULL");
+  if (M % 128 != 0 || N % 128 != 0 || K0 % 64 != 0 || K1 % 64 != 0 || K0 <= 0)
+    return fail("dense: shape constraint violated (M%%128, N%%128, K%%64)");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  DenseLaunch d;
+  memset(&d, 0, sizeof(d));
+  d.A[0] = static_cast<const __half*>(A0);
+  d.B[0] = static_cast<const __half*>(B0);
+  d.A[1] = static_cast<const __half*>(A1);
+  d.B[1] = static_cast<const __half*>(B1);
+  d.K[0] = K0;
+  d.K[1] = (A1 && B1) ? K1 : 0;
+  d.lda[0] = K0;
+  d.lda[1] = K1;
+  d.C = static_cast<__half*>(C);
+  d.ldc = N;
+  d.bias = bias;
+  d.M = M;
+  d.N = N;
+  d.BN = (N % 256 == 0) ? 256 : 128;
+  d.relu = relu;
+  if (use_simt) {
+    CK(launch_dense_simt(d, s));
+  } else {
+    const int nseg = d.K[1] > 0 ? 2 : 1;
+    for (int i = 0; i < nseg; ++i) {
+      if (make_tmap_2d(c, &d.tmA[i], d.A[i], (uint64_t)M, (uint64_t)d.K[i], (uint64_t)d.K[i], 128)) return 1;
+      if (make_tmap_2d(c, &d.tmB[i], d.B[i], (uint64_t)N, (uint64_t)d.K[i], (uint64_t)d.K[i], d.BN)) return 1;
+    }
+    if (make_tmap_2d(c, &d.tmC, d.C, (uint64_t)M, (uint64_t)N, (uint64_t)N, 128)) return 1;
+    CK(launch_dense_tc(d, c->num_sms, s));
+  }
+  c->launches++;
+  return 0;
+}
+
+}  // extern "C"

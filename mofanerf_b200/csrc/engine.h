@@ -1,0 +1,67 @@
+// Internal declarations shared by the engine's translation units (not part of the C ABI).
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mofa {
+
+// ---- dense layer (tcgen05 kernel and SIMT verification kernel) ----------------------------------
+struct DenseLaunch {
+  CUtensorMap tmA[2];   // activations  [M, K_seg] fp16, box {64, 128}, SWIZZLE_128B
+  CUtensorMap tmB[2];   // weights      [N, K_seg] fp16, box {64, BN},  SWIZZLE_128B
+  CUtensorMap tmC;      // output       [M, N]     fp16, box {64, 128}, SWIZZLE_128B
+  // raw pointers of the same operands (SIMT verification path)
+  const __half* A[2];
+  const __half* B[2];
+  __half* C;
+  int lda[2];           // row pitch (elements) of A segments
+  int ldc;              // row pitch of C
+  int K[2];             // K of each segment (multiple of 64; K[1] == 0 when single segment)
+  const float* bias;    // [N] fp32 or nullptr
+  int64_t M;            // multiple of 128
+  int N;                // multiple of BN
+  int BN;               // 128 or 256
+  int relu;
+};
+
+cudaError_t launch_dense_tc(const DenseLaunch& L, int num_sms, cudaStream_t stream);
+cudaError_t launch_dense_simt(const DenseLaunch& L, cudaStream_t stream);
+cudaError_t dense_tc_configure();   // one-time cudaFuncSetAttribute for the kernel instantiations
+
+// ---- element-wise / per-ray kernels (sampling.cu) -----------------------------------------------
+struct RayView {
+  const float* rays;   // [n, stride]
+  int stride;
+};
+
+cudaError_t launch_zvals_coarse(const float* rays, int stride, int64_t n, int S, int lindisp, float perturb,
+                                const float* t_rand, uint64_t seed, int64_t ray_offset, float* z,
+                                cudaStream_t s);
+// points from rays + z  ->  fp16 PE rows X0 [P,64] (63 features + 0) and view PE rows V [P,64] (27 + 0)
+cudaError_t launch_encode_rays(const float* rays, int stride, const float* z, int64_t n, int S,
+                               int multires, int multires_views, __half* X0, __half* V, cudaStream_t s);
+// explicit points (run_network): pts [P,3], viewdirs [P,3]
+cudaError_t launch_encode_points(const float* pts, const float* viewdirs, int64_t P, int multires,
+                                 int multires_views, __half* X0, __half* V, cudaStream_t s);
+cudaError_t launch_embed_f32(const float* x, int64_t n, int multires, float* out, cudaStream_t s);
+// out[p*4 + off + j] = A[p,:]·Wh[j,:] + b[j]    (alpha_linear / rgb_linear)
+cudaError_t launch_head(const __half* A, int K, const float* Wh, const float* b, int nout, float* raw,
+                        int off, int64_t P, cudaStream_t s);
+cudaError_t launch_composite(const float* raw, const float* z, const float* rays_d, int d_stride,
+                             const float* noise, float noise_std, uint64_t seed, int64_t ray_offset,
+                             int64_t n, int S, int white_bkgd, float* rgb, float* disp, float* acc,
+                             float* weights, float* depth, cudaStream_t s);
+cudaError_t launch_sample_pdf_merge(const float* z, const float* weights, const float* u, int det,
+                                    uint64_t seed, int64_t ray_offset, int64_t n, int S, int Ni,
+                                    float* z_samples, float* z_merged, float* z_std, cudaStream_t s);
+// dst[n, kpad] (fp16) = src[n, c0 : c0+k] (fp32, row pitch ld), zero padded to kpad columns
+cudaError_t launch_pack_weight(const float* src, int ld, int c0, int k, int kpad, int nrows, __half* dst,
+                               cudaStream_t s);
+// out[n] = b[n] + sum_j Wc[n*ld + c0 + j] * lat[j]
+cudaError_t launch_fold_bias(const float* Wsrc, int ld, int c0, int nlat, const float* b, const float* lat,
+                             int nrows, float* out, cudaStream_t s);
+cudaError_t launch_copy_f32(const float* src, float* dst, int64_t n, cudaStream_t s);
+
+}  // namespace mofa

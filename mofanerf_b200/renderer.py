@@ -1,0 +1,299 @@
+"""B200Renderer — drop-in for the reference's `models.render_class.myRenderer` (models/render_class.py:40-437).
+
+Same constructor, methods, argument names/meaning and return structures, so run_fit.py (render_fitting),
+run_train.py (render) and render_refine_trainSet.py (render_path) can call it unchanged once
+`mofanerf_b200.install()` has swapped it in.  Everything from `render_rays` downward runs in the sm_100a
+engine (libmofa_b200.so): there is no PyTorch or CPU fallback for the per-ray work.
+
+What stays PyTorch (O(1) per image): ray generation, the texture encoder,
+the StyleModule expression modulation.
+"""
+from __future__ import annotations
+
+import os
+import time
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import distributed as mdist
+from .engine import Engine, get_engine
+from .nets import StyleModule, TexEncoder
+from .rays import get_rays, ndc_rays, pack_rays
+
+to8b = lambda x: (255 * np.clip(x, 0, 1)).astype(np.uint8)  # noqa: E731  (tools/run_nerf_helpers.py:11)
+
+
+class lossesLog:
+    """models/render_class.py:13-37 (the texture encoder returns no losses, so out() is 0)."""
+
+    def __init__(self, lossesList, Weight):
+        self.lossesNameList = lossesList
+        self.lossesDict = {n: 0 for n in lossesList}
+        self.chunkDict = {n: 0 for n in lossesList}
+        self.lossesWeight = {n: Weight[i] for i, n in enumerate(lossesList)}
+
+    def update(self, lossesList, chunk):
+        for name, value in lossesList.items():
+            self.lossesDict[name] += torch.sum(value)
+            self.chunkDict[name] += chunk
+
+    def out(self):
+        loss = 0
+        for name, value in self.lossesDict.items():
+            if value != 0:
+                loss += value / self.chunkDict[name] * self.lossesWeight[name]
+            self.lossesDict[name] = 0
+            self.chunkDict[name] = 0
+        return loss
+
+
+def _needs_grad(*tensors) -> bool:
+    return torch.is_grad_enabled() and any(torch.is_tensor(t) and t.requires_grad for t in tensors)
+
+
+class B200Renderer(torch.nn.Module):
+    def __init__(self, embed_fn=None, embeddirs_fn=None, netchunk=1024 * 64, uvCodesLen=256, expCodesLen=4,
+                 input_ch=3, shapeCodes=50):
+        super().__init__()
+        # embed_fn / embeddirs_fn / netchunk are accepted for signature compatibility: the engine computes
+        # the encodings in-kernel and needs no point chunking (no [P, W] activations in Python).
+        self.embed_fn = embed_fn
+        self.embeddirs_fn = embeddirs_fn
+        self.netchunk = netchunk
+        self.texEncoder = TexEncoder(uvCodesLen)
+        self.lossList = ["loss_deformReg", "loss_kldiv", "loss_offsets"]
+        self.lossWeight = [0.05, 1, 0.01]
+        self.lossLog = lossesLog(self.lossList, self.lossWeight)
+        self.idSpecificMod = StyleModule()
+        self.is_run_fineNet = True
+        dev = "cuda" if torch.cuda.is_available() else "cpu"
+        self.expCodes_Sigma = [torch.rand([1, expCodesLen]).to(dev) for _ in range(20)]  # :53-58
+        for latent in self.expCodes_Sigma:
+            latent.requires_grad = True
+        self._engine: Optional[Engine] = None
+        self.shard_rays = os.environ.get("MOFA_B200_SHARD", "0") == "1"
+        self.seed = 0
+        self._call = 0
+
+    # ------------------------------------------------------------------ reference surface
+    def grad_parameter(self):
+        grad_vars = []
+        grad_vars += self.expCodes_Sigma
+        if self.texEncoder is not None:
+            grad_vars += list(self.texEncoder.parameters())
+        if self.idSpecificMod is not None:
+            grad_vars += list(self.idSpecificMod.parameters())
+        return grad_vars
+
+    def engine(self, device=None) -> Engine:
+        if self._engine is None:
+            self._engine = get_engine(device)
+        return self._engine
+
+    def _exp_mod(self):
+        """exp_scale * expCodes_Sigma[expType] + exp_bias   (models/render_class.py:75,80-81)."""
+        shape_row = self.shapeCodes[0, :].reshape(1, -1)
+        dev = next(self.idSpecificMod.parameters()).device
+        exp_scale, exp_bias = self.idSpecificMod(shape_row.to(dev))
+        code = self.expCodes_Sigma[self.expType].to(dev)
+        return exp_scale * code + exp_bias
+
+    def _prepare(self, network_fn, network_fine, device):
+        eng = self.engine(device)
+        eng.load_network(0, network_fn)
+        if network_fine is not None:
+            eng.load_network(1, network_fine)
+        with torch.no_grad():
+            eng.set_latents(self.shapeCodes[0, :], self._exp_mod(), self.decoding_texCodes)
+        return eng
+
+    def run_network(self, inputs, viewdirs, fn=None):
+        """models/render_class.py:69-94: query `fn` at explicit points.  `fn` is the coarse or fine net."""
+        if _needs_grad(inputs, viewdirs):
+            raise NotImplementedError("B200Renderer.run_network: autograd through the engine is not implemented yet")
+        eng = self.engine(inputs.device)
+        which = 0 if eng._net_keys[0] == Engine._key(fn) else 1
+        eng.load_network(which, fn)
+        with torch.no_grad():
+            eng.set_latents(self.shapeCodes[0, :], self._exp_mod(), self.decoding_texCodes)
+        vd = viewdirs[:, None].expand(inputs.shape) if viewdirs.dim() == inputs.dim() - 1 else viewdirs
+        return eng.run_network(which, inputs, vd)
+
+    def batchify(self, fn, chunk):
+        raise NotImplementedError("batchify(): point chunking is internal to the CUDA engine")
+
+    def batchify_rays(self, chunk=1024 * 32, **kwargs):
+        """models/render_class.py:111-123."""
+        all_ret = {}
+        for i in range(0, self.rays.shape[0], chunk):
+            ret = self.render_rays([i, i + chunk], **kwargs)
+            for k in ret:
+                all_ret.setdefault(k, []).append(ret[k])
+        return {k: torch.cat(all_ret[k], 0) for k in all_ret}
+
+    def render_rays(self, ray_batch, network_fn, N_samples, retraw=False, lindisp=False, perturb=0.,
+                    N_importance=0, network_fine=None, white_bkgd=False, raw_noise_std=0., network_query_fn=None,
+                    verbose=False, pytest=False, t_rand=None, u=None, noise_c=None, noise_f=None, want_aux=False,
+                    gemm_simt=False):
+        """models/render_class.py:239-352.  Extra keyword-only inputs (t_rand/u/noise_*) feed explicit random
+        numbers for parity tests; with pytest=True they default to the reference's seeded numpy draws."""
+        rays = self.rays[ray_batch[0]:ray_batch[1]]
+        if rays.shape[-1] < 11:
+            raise NotImplementedError("use_viewdirs=False is not supported (the MoFaNeRF nets require view dirs)")
+        exp_in = self.expCodes_Sigma[self.expType] if self.expType == 20 else None   # caller-supplied code (fitting)
+        if _needs_grad(rays, self.shapeCodes, self.decoding_texCodes, exp_in):
+            raise NotImplementedError(
+                "B200Renderer: gradients through render_rays (fitting/training) are SURVEY.md §8 row f1 — "
+                "forward only in this version; call under torch.no_grad()")
+        n = rays.shape[0]
+        fine = N_importance > 0 and self.is_run_fineNet
+        if pytest:  # models/render_class.py:308-311,465-468; tools/run_nerf_helpers.py:218-226
+            if perturb > 0. and t_rand is None:
+                np.random.seed(0)
+                t_rand = torch.Tensor(np.random.rand(n, N_samples))
+            if perturb > 0. and fine and u is None:
+                np.random.seed(0)
+                u = torch.Tensor(np.random.rand(n, N_importance))
+            if raw_noise_std > 0.:
+                if noise_c is None:
+                    np.random.seed(0)
+                    noise_c = torch.Tensor(np.random.rand(n, N_samples) * raw_noise_std)
+                if fine and noise_f is None:
+                    np.random.seed(0)
+                    noise_f = torch.Tensor(np.random.rand(n, N_samples + N_importance) * raw_noise_std)
+        eng = self._prepare(network_fn, network_fine, rays.device)
+        self._call += 1
+        return eng.render_rays(rays, N_samples, N_importance, run_fine=self.is_run_fineNet,
+                               fine_net=(1 if network_fine is not None else 0), perturb=float(perturb),
+                               raw_noise_std=float(raw_noise_std), lindisp=bool(lindisp),
+                               white_bkgd=bool(white_bkgd), retraw=bool(retraw),
+                               seed=self.seed * 1000003 + self._call, t_rand=t_rand, u=u, noise_c=noise_c,
+                               noise_f=noise_f, want_aux=want_aux, gemm_simt=gemm_simt)
+
+    # ------------------------------------------------------------------ render / render_fitting
+    def _rays_from_args(self, H, W, K, rays, c2w, ndc, near, far, use_viewdirs, c2w_staticcam):
+        if c2w is not None:
+            rays_o, rays_d = get_rays(H, W, K, c2w)
+        else:
+            rays_o, rays_d = rays
+        viewdirs = None
+        if use_viewdirs:
+            viewdirs = rays_d
+            if c2w_staticcam is not None:
+                rays_o, rays_d = get_rays(H, W, K, c2w_staticcam)
+            viewdirs = viewdirs / torch.norm(viewdirs, dim=-1, keepdim=True)
+            viewdirs = torch.reshape(viewdirs, [-1, 3]).float()
+        sh = rays_d.shape
+        if ndc:
+            rays_o, rays_d = ndc_rays(H, W, K[0][0], 1., rays_o, rays_d)
+        return pack_rays(rays_o, rays_d, near, far, viewdirs), sh
+
+    def _finish(self, all_ret, sh):
+        for k in all_ret:
+            all_ret[k] = torch.reshape(all_ret[k], list(sh[:-1]) + list(all_ret[k].shape[1:]))
+        k_extract = ['rgb_map', 'disp_map', 'acc_map']
+        ret_list = [all_ret[k] for k in k_extract]
+        ret_dict = {k: all_ret[k] for k in all_ret if k not in k_extract}
+        if self.lossList is not None:
+            ret_dict['losses'] = self.lossLog.out()
+        return ret_list + [ret_dict]
+
+    def _to_device(self, rays):
+        if rays.device.type != "cuda":
+            if not torch.cuda.is_available():
+                raise RuntimeError("B200Renderer needs a CUDA device (sm_100a); there is no CPU path")
+            rays = rays.cuda(non_blocking=True)
+        return rays
+
+    def _render_all(self, chunk, sh, **kwargs):
+        if self.shard_rays and torch.distributed.is_available() and torch.distributed.is_initialized():
+            full = self.rays
+
+            def local_fn(r):
+                self.rays = r
+                return self.batchify_rays(chunk, **kwargs)
+
+            out = mdist.render_sharded(local_fn, full, keys=("rgb_map", "disp_map", "acc_map"))
+            self.rays = full
+            all_ret = {k: v for k, v in out.items() if not k.endswith("_local")}
+        else:
+            all_ret = self.batchify_rays(chunk, **kwargs)
+        return self._finish(all_ret, sh)
+
+    def render(self, H, W, K, chunk=1024 * 32, rays=None, c2w=None, ndc=True, shapeCodes=None, uvMap=None,
+               expType=None, near=0., far=1., use_viewdirs=False, c2w_staticcam=None, **kwargs):
+        """models/render_class.py:125-197 -> [rgb_map, disp_map, acc_map, extras]."""
+        rays, sh = self._rays_from_args(H, W, K, rays, c2w, ndc, near, far, use_viewdirs, c2w_staticcam)
+        self.shapeCodes = shapeCodes
+        self.rays = self._to_device(rays)
+        self.uvMap = uvMap
+        self.expType = expType
+        enc_dev = next(self.texEncoder.parameters()).device
+        self.decoding_texCodes, enlosses = self.texEncoder(uvMap.permute([2, 0, 1]).unsqueeze(0).to(enc_dev),
+                                                           self.lossList)                       # :184
+        self.lossLog.update(enlosses, 1)
+        return self._render_all(chunk, sh, **kwargs)
+
+    def render_fitting(self, H, W, K, chunk=1024 * 32, rays=None, c2w=None, ndc=True, shapeCodes=None,
+                       uvCodes=None, expType=20, expCodes=None, near=0., far=1., use_viewdirs=False,
+                       c2w_staticcam=None, network_query_fn=None, **kwargs):
+        """models/render_class.py:354-437 -> [rgb_map, disp_map, acc_map, extras]."""
+        kwargs['network_fine'].eval()
+        kwargs['network_fn'].eval()
+        rays, sh = self._rays_from_args(H, W, K, rays, c2w, ndc, near, far, use_viewdirs, c2w_staticcam)
+        self.shapeCodes = shapeCodes
+        self.rays = self._to_device(rays)
+        self.expType = expType
+        if len(self.expCodes_Sigma) == 20:
+            self.expCodes_Sigma.append(expCodes)
+        else:
+            self.expCodes_Sigma[20] = expCodes
+        self.decoding_texCodes = uvCodes
+        return self._render_all(chunk, sh, **kwargs)
+
+    def render_path(self, render_poses, hwf, K, chunk, render_kwargs, uvMap=None, expType=None, gt_imgs=None,
+                    savedir=None, render_factor=0, shapeCodes=None, name=None):
+        """models/render_class.py:199-237."""
+        H, W, focal = hwf
+        if render_factor != 0:
+            H = H // render_factor
+            W = W // render_factor
+            focal = focal / render_factor
+        rgbs, disps = [], []
+        t = time.time()
+        if savedir is not None:
+            filename = os.path.join(savedir, '{}.png'.format(name))
+            if os.path.exists(filename):
+                print("exists")
+                return 0, 0
+        for i, c2w in enumerate(render_poses):
+            print(i, time.time() - t)
+            t = time.time()
+            rgb, disp, acc, _ = self.render(H, W, K, chunk=chunk, c2w=c2w[:3, :4],
+                                            shapeCodes=shapeCodes[i, :].reshape(1, -1), uvMap=uvMap[i, :],
+                                            expType=expType[i], **render_kwargs)
+            rgbs.append(rgb.cpu().numpy())
+            disps.append(disp.cpu().numpy())
+            if savedir is not None:
+                rgb8 = to8b(rgbs[-1])
+                fn = os.path.join(savedir, '{}.png'.format(name) if name is not None else '{:03d}.png'.format(i))
+                _imwrite(fn, rgb8)
+        return np.stack(rgbs, 0), np.stack(disps, 0)
+
+
+def _imwrite(path, img8):
+    try:
+        import imageio
+        imageio.imwrite(path, img8)
+    except Exception:
+        from PIL import Image
+        Image.fromarray(img8).save(path)
+
+
+def install() -> None:
+    """Swap the engine into an importable reference tree: after this, tools/create_model_condition.py:48
+    constructs a B200Renderer, and run_fit.py / run_train.py / render_refine_trainSet.py run unchanged."""
+    import models.render_class as rc  # the reference's module (must be on sys.path)
+    rc.myRenderer = B200Renderer

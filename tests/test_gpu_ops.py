@@ -1,0 +1,133 @@
+"""GPU parity, op level: each stage of the CUDA engine against the oracle and the reference-generated
+fixtures, through the C ABI (mofanerf_b200.Engine -> libmofa_b200.so).
+
+Stated tolerances:
+  * fp32 stages (encoding, compositing, resampling): 5e-6 .. 1e-4 absolute — CUDA libm vs CPU libm ulps
+    and reduction order only;
+  * dense layer: fp16 operands, fp32 accumulate, fp16 output — compared with an fp32 matmul of the SAME
+    fp16-rounded operands: |err| <= 2e-3 * |ref| + 2e-3 (one fp16 output rounding + accumulation order).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import mofa_oracle as O
+from tests.helpers import GOLDEN, assert_close_nan
+
+pytestmark = pytest.mark.gpu
+
+OPS = np.load(f"{GOLDEN}/ops.npz")
+
+
+def T(k):
+    return torch.from_numpy(OPS[k])
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from mofanerf_b200 import get_engine
+    return get_engine("cuda:0")
+
+
+def test_embed_matches_reference_fixture(eng):
+    x = T("pe_x")
+    assert_close_nan(eng.embed(x, 10).cpu(), T("pe_out10"), 5e-6, what="embed L=10")
+    assert_close_nan(eng.embed(x, 4).cpu(), T("pe_out4"), 5e-6, what="embed L=4")
+
+
+@pytest.mark.parametrize("wb", [0, 1])
+def test_raw2outputs_fixture(eng, wb):
+    out = eng.raw2outputs(T("r2o_raw"), T("r2o_z"), T("r2o_d"), None, bool(wb))
+    for nm, v in zip(("rgb", "disp", "acc", "weights", "depth"), out):
+        assert_close_nan(v.cpu(), T(f"r2o_wb{wb}_{nm}"), 2e-5, 2e-5, what=f"raw2outputs:{nm}")
+    assert torch.isnan(out[1][:8]).all()
+
+
+@pytest.mark.parametrize("S", [1, 32, 33, 96, 128, 256])
+def test_raw2outputs_sizes(eng, S):
+    g = torch.Generator().manual_seed(S)
+    n = 37
+    raw = torch.randn(n, S, 4, generator=g) * 2
+    z = torch.sort(torch.rand(n, S, generator=g) * 18 + 8, -1)[0]
+    d = torch.randn(n, 3, generator=g)
+    noise = torch.rand(n, S, generator=g)
+    ref = O.raw2outputs(raw, z, d, noise, False)
+    out = eng.raw2outputs(raw, z, d, noise, False)
+    for nm, a, b in zip(("rgb", "disp", "acc", "weights", "depth"), out, ref):
+        assert_close_nan(a.cpu(), b, 2e-5, 2e-5, what=f"S={S}:{nm}")
+
+
+def test_sample_pdf_fixture(eng):
+    z = T("r2o_z")
+    w = T("r2o_wb0_weights")
+    zs, zm, sd = eng.sample_pdf_merge(z, w, 64, None)
+    assert_close_nan(zs.cpu(), T("pdf_det"), 1e-4, what="sample_pdf det")
+    ref_m = torch.sort(torch.cat([z, T("pdf_det")], -1), -1)[0]
+    assert_close_nan(zm.cpu(), ref_m, 1e-4, what="merged z")
+    assert_close_nan(sd.cpu(), torch.std(T("pdf_det"), dim=-1, unbiased=False), 1e-4, what="z_std")
+    zs, zm, _ = eng.sample_pdf_merge(z, w, 64, T("pdf_u"))
+    assert_close_nan(zs.cpu(), T("pdf_rand_pytest"), 1e-4, what="sample_pdf explicit u")
+    assert bool((zm[:, 1:] >= zm[:, :-1]).all()), "merged depths must be sorted"
+
+
+@pytest.mark.parametrize("S,Ni", [(32, 64), (64, 128), (17, 40)])
+def test_sample_pdf_sizes(eng, S, Ni):
+    g = torch.Generator().manual_seed(S * 1000 + Ni)
+    n = 29
+    z = torch.sort(torch.rand(n, S, generator=g) * 18 + 8, -1)[0]
+    w = torch.rand(n, S, generator=g) ** 4
+    ref = O.sample_pdf(0.5 * (z[:, 1:] + z[:, :-1]), w[:, 1:-1], Ni, det=True)
+    zs, zm, sd = eng.sample_pdf_merge(z, w, Ni, None)
+    assert_close_nan(zs.cpu(), ref, 1e-4, what="samples")
+    assert_close_nan(zm.cpu(), torch.sort(torch.cat([z, ref], -1), -1)[0], 1e-4, what="merged")
+
+
+def _dense_ref(A0, B0, bias, A1=None, B1=None, relu=True):
+    acc = A0.half().float() @ B0.half().float().t()
+    if A1 is not None:
+        acc = acc + A1.half().float() @ B1.half().float().t()
+    if bias is not None:
+        acc = acc + bias
+    return torch.relu(acc) if relu else acc
+
+
+@pytest.mark.parametrize("M,N,K0,K1", [(128, 256, 64, 0), (256, 128, 64, 0), (384, 256, 256, 0),
+                                       (1024, 1024, 1024, 0), (640, 256, 256, 256), (512, 512, 64, 1024),
+                                       (128 * 301, 1024, 1024, 1024)])
+@pytest.mark.parametrize("simt", [False, True])
+def test_dense_layer(eng, M, N, K0, K1, simt):
+    if simt and M > 4096:
+        pytest.skip("verification kernel: small shapes only")
+    g = torch.Generator().manual_seed(M + N + K0 + K1)
+    dev = "cuda:0"
+    A0 = (torch.randn(M, K0, generator=g) * 0.5).to(dev)
+    B0 = (torch.randn(N, K0, generator=g) * 0.05).to(dev)
+    bias = torch.randn(N, generator=g).to(dev) * 0.1
+    A1 = B1 = None
+    if K1:
+        A1 = (torch.randn(M, K1, generator=g) * 0.5).to(dev)
+        B1 = (torch.randn(N, K1, generator=g) * 0.05).to(dev)
+    for relu in (True, False):
+        out = eng.dense(A0, B0, bias, A1, B1, relu=relu, simt=simt).float()
+        ref = _dense_ref(A0, B0, bias, A1, B1, relu)
+        err = (out - ref).abs()
+        lim = 2e-3 * ref.abs() + 2e-3
+        bad = int((err > lim).sum())
+        assert bad == 0, (f"dense {'simt' if simt else 'tcgen05'} M={M} N={N} K={K0}+{K1} relu={relu}: {bad} bad, "
+                          f"max err {err.max().item():.3e}, ref absmax {ref.abs().max().item():.3e}, "
+                          f"first bad idx {torch.nonzero(err > lim)[:4].tolist()}")
+
+
+def test_dense_linearity(eng):
+    """Size-independent property at a full-size tile count: dense(A, B) with relu off is linear in A."""
+    g = torch.Generator().manual_seed(3)
+    dev = "cuda:0"
+    M, N, K = 128 * 592, 1024, 1024          # 592 x 4 tiles = 16 waves of 148 CTAs
+    A = (torch.randn(M, K, generator=g) * 0.25).half().to(dev)
+    B = (torch.randn(N, K, generator=g) * 0.05).half().to(dev)
+    y1 = eng.dense(A, B, None, relu=False).float()
+    y2 = eng.dense(A * 2, B, None, relu=False).float()     # exact scaling in fp16 => exactly 2x
+    assert torch.equal(y2, 2 * y1)
+    rows = torch.randint(0, M, (64,), generator=g)
+    ref = A[rows].float() @ B.float().t()
+    assert (y1[rows] - ref).abs().max().item() < 2e-3 * ref.abs().max().item() + 2e-3
