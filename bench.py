@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py — rays/s of the MoFaNeRF ray-marching hot path on B200 (BASELINE.json's metric).
+
+One "step" = one full pass of the hot path over one synthetic 800x800 frame (640 000 rays), FULL pipeline
+= the reference's default configuration (configs/exp_mofanerf.txt): 64 coarse samples through the coarse
+net (D=8, W=256) + 128 fine samples through the fine net (D=10, W=1024) per ray, fp16 tensor-core dense
+layers with fp32 accumulation, everything else fp32.  Random-init weights of the real architecture and
+synthetic latents (no network for checkpoints) — cost is data independent (no early termination in
+models/render_class.py:284-352).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          # engine arm (default N=1)
+  python bench.py --impl reference ...                          # the reference algorithm on the host CPU cores
+
+Multi-GPU (launched by torchrun, one rank per GPU): the frame's rays are sharded by contiguous row-major
+range, each rank renders its range, one NCCL all-gather rebuilds the RGB tile (the only collective).
+Total work is fixed => "scaling": "strong".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FLOP_COARSE_PT = 3187200.0      # 2*in*out over the coarse net's 23 nn.Linear
+FLOP_FINE_PT = 54953984.0       # ... the fine net's 27 nn.Linear
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--H", type=int, default=800)
+    ap.add_argument("--W", type=int, default=800)
+    ap.add_argument("--n-samples", type=int, default=64)
+    ap.add_argument("--n-importance", type=int, default=64)
+    ap.add_argument("--chunk-rays", type=int, default=0, help="engine-internal rays per pass (0 = default)")
+    ap.add_argument("--cpu-sample-rays", type=int, default=0, help="rays in the CPU baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def synth_inputs(H, W, seed=0):
+    """SURVEY.md §8(d) synthetic inputs: camera pose_spherical(30, 0, 16), focal 1200*H/512, near 8, far 26;
+    shape ~ N(0, 0.034), texture ~ N(0.14, 0.26), expression ~ U[0,1)."""
+    from mofanerf_b200.rays import get_rays, pose_spherical
+    g = torch.Generator().manual_seed(seed + 100)
+    shape = torch.randn(1, 50, generator=g) * 0.034
+    tex = 0.14 + 0.26 * torch.randn(256, generator=g)
+    exp = torch.rand(1, 30, generator=g)
+    focal = 1200.0 * H / 512.0
+    K = np.array([[focal, 0, 0.5 * W], [0, focal, 0.5 * H], [0, 0, 1]])
+    c2w = pose_spherical(30.0, 0.0, 16.0)
+    ro, rd = get_rays(H, W, K, c2w[:3, :4])
+    return shape, tex, exp, ro.reshape(-1, 3).contiguous(), rd.reshape(-1, 3).contiguous()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc, self.thread = index, [], None, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        def pump():
+            for line in self.proc.stdout:
+                self.rows.append(line.strip())
+        self.thread = threading.Thread(target=pump, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            p = [x.strip() for x in r.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0])); mx.append(float(p[1])); pw.append(float(p[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained; kernel timed inside a long step)"
+    return 1400.0, "fallback (B200_PROFILING.md: ~1.4 PFLOP/s sustained)"
+
+
+def cpu_baseline(n_s, n_i, sample_rays, max_seconds=25.0):
+    """The oracle port (fp32 PyTorch restatement of the reference, oracle/mofa_oracle.py) timed on the host
+    cores on a bounded sample of the same workload."""
+    from oracle import mofa_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    c, f, s = O.build_nets(0)
+    shape, tex, exp, ro, rd = synth_inputs(64, 64)
+    em = O.expression_mod(s, shape, exp)
+    n = sample_rays if sample_rays > 0 else 64
+    best = None
+    t_total = 0.0
+    while True:
+        idx = torch.linspace(0, ro.shape[0] - 1, n).long()
+        rays = O.make_ray_batch(ro[idx], rd[idx], 8.0, 26.0)
+        t0 = time.perf_counter()
+        O.render_rays(rays, c, f, shape, em, tex, N_samples=n_s, N_importance=n_i)
+        dt = time.perf_counter() - t0
+        t_total += dt
+        best = (n, dt)
+        if sample_rays > 0 or dt >= 8.0 or t_total >= max_seconds or n >= 4096:
+            break
+        n = min(4096, int(n * max(2.0, min(8.0, 10.0 / max(dt, 1e-3)))))
+    n, dt = best
+    return {"value": n / dt, "unit": "rays/s", "cores": cores, "kind": "port",
+            "sample": f"{n} rays x ({n_s} coarse + {n_s + n_i} fine) samples, fp32, oracle/mofa_oracle.py, {dt:.1f} s"}
+
+
+def run_reference(args, rank, world):
+    """Reference arm: the reference's algorithm on the host CPU (the oracle port: /root/reference does not
+    exist on the GPU box).  Rank 0 only."""
+    if rank != 0:
+        return
+    from oracle import mofa_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    c, f, s = O.build_nets(0)
+    shape, tex, exp, ro, rd = synth_inputs(args.H, args.W)
+    em = O.expression_mod(s, shape, exp)
+    n = args.cpu_sample_rays if args.cpu_sample_rays > 0 else 256
+    idx = torch.linspace(0, ro.shape[0] - 1, n).long()
+    rays = O.make_ray_batch(ro[idx], rd[idx], 8.0, 26.0)
+    times = []
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        O.render_rays(rays, c, f, shape, em, tex, N_samples=args.n_samples, N_importance=args.n_importance)
+        if i >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    ms = 1e3 * sum(times) / len(times)
+    val = n / (ms / 1e3)
+    sample = f"{n} rays of the {args.H}x{args.W} frame per step, fp32 PyTorch on {cores} host threads"
+    line = {"impl": "reference", "metric": "rays/sec at 800x800x64 samples (FULL: 64 coarse + 128 fine evaluations/ray)",
+            "value": val, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(args),
+            "cpu_baseline": {"value": val, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args):
+    return {"workload": f"{args.H}x{args.W} frame ({args.H * args.W} rays), FULL pipeline: N_samples={args.n_samples} "
+                        f"coarse (D=8,W=256) + {args.n_samples + args.n_importance} fine (D=10,W=1024) evaluations per ray, "
+                        "single identity, perturb=0 (render_kwargs_test)",
+            "rays_per_step": args.H * args.W, "parallelism": f"ray-sharded x{args.gpus}",
+            "l2": "working set (activation buffers, >1 GB per pass) >> 126 MB L2; 256 MB scratch write between timed steps"}
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (engine arm) needs a B200; there is no CPU path. Use --impl reference for the CPU arm.")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    import __graft_entry__
+    __graft_entry__.build()
+    from mofanerf_b200 import B200Renderer, nets
+    from mofanerf_b200.distributed import all_gather_rows, shard_range
+
+    coarse, fine, style = nets.build_nets(0, device=dev)
+    shape, tex, exp, ro, rd = synth_inputs(args.H, args.W)
+    n_total = ro.shape[0]
+    lo, hi = shard_range(n_total, rank, world)
+    renderer = B200Renderer(expCodesLen=30).to(dev)
+    renderer.idSpecificMod.load_state_dict(style.state_dict())
+    eng = renderer.engine(dev)
+    eng.chunk_rays = args.chunk_rays
+    kw = dict(near=8.0, far=26.0, use_viewdirs=True, ndc=False, network_fn=coarse, network_fine=fine,
+              N_samples=args.n_samples, N_importance=args.n_importance, perturb=0.0, raw_noise_std=0.0)
+    shape_d, tex_d, exp_d = shape.to(dev), tex.to(dev), exp.to(dev)
+
+    # device-resident inputs for `value`; pinned host inputs for `e2e`
+    ro_d, rd_d = ro[lo:hi].to(dev), rd[lo:hi].to(dev)
+    ro_h, rd_h = ro[lo:hi].pin_memory(), rd[lo:hi].pin_memory()
+    rgb_h = torch.empty(n_total, 3).pin_memory()
+    scratch = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step_device():
+        with torch.no_grad():
+            rgb, disp, acc, _ = renderer.render_fitting(args.H, args.W, None, chunk=1 << 30, rays=(ro_d, rd_d),
+                                                        shapeCodes=shape_d, uvCodes=tex_d, expType=20,
+                                                        expCodes=exp_d, **kw)
+            if world > 1:
+                rgb = all_gather_rows(rgb, n_total)
+        return rgb
+
+    def step_e2e():
+        with torch.no_grad():
+            a, b = ro_h.to(dev, non_blocking=True), rd_h.to(dev, non_blocking=True)
+            rgb, disp, acc, _ = renderer.render_fitting(args.H, args.W, None, chunk=1 << 30, rays=(a, b),
+                                                        shapeCodes=shape_d, uvCodes=tex_d, expType=20,
+                                                        expCodes=exp_d, **kw)
+            if world > 1:
+                rgb = all_gather_rows(rgb, n_total)
+            rgb_h.copy_(rgb, non_blocking=True)
+        return rgb
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps, profile=False):
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        barrier()
+        for s0, s1 in ev:
+            scratch.fill_(1)          # evict L2 between timed steps (not timed)
+            if world > 1:
+                dist.barrier()
+            s0.record()
+            fn()
+            s1.record()
+        barrier()
+        ms = [a.elapsed_time(b) for a, b in ev]
+        t = torch.tensor([sum(ms) / steps], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)     # max over ranks
+        return float(t.item())
+
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = eng.launch_count
+    eng.profile_enable(True)
+    ms_dev = timed(step_device, args.steps)
+    prof = eng.profile_read()
+    eng.profile_enable(False)
+    launches = (eng.launch_count - l0) // max(1, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    for _ in range(max(1, args.warmup // 2)):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    rays_per_s = n_total / (ms_dev / 1e3)
+    e2e_rays = n_total / (ms_e2e / 1e3)
+    peak_tf, peak_src = measured_peak()
+    fine_p = prof[1]
+    ach_tf = (fine_p["algo_flops"] / (fine_p["ms"] / 1e3)) / 1e12 if fine_p["ms"] > 0 else 0.0
+    traffic = None
+    ncu_json = os.path.join(ROOT, "profiles", "ncu_dense_tc_summary.json")
+    if os.path.exists(ncu_json):
+        try:
+            traffic = json.load(open(ncu_json)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    n_loc = hi - lo
+    flop_step = n_loc * (args.n_samples * FLOP_COARSE_PT + (args.n_samples + args.n_importance) * FLOP_FINE_PT)
+    line = {
+        "metric": "rays/sec at 800x800x64 samples (FULL: 64 coarse + 128 fine evaluations/ray)",
+        "value": rays_per_s, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f16 operands / f32 accumulate (dense layers); f32 elsewhere", "data": "synthetic",
+        "config": workload_config(args),
+        "clocks": clocks,
+        "e2e": {"value": e2e_rays, "unit": "rays/s", "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": int(n_loc * 6 * 4), "d2h_bytes_per_step": int(n_total * 3 * 4),
+                "api": "B200Renderer.render_fitting(rays=pinned host tensors) -> rgb copied to pinned host"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "tensor", "kernel": "dense_tc_kernel<256,4> (fine-net layers, tcgen05 kind::f16)",
+                     "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
+                     "peak_source": peak_src, "traffic": traffic,
+                     "launches_per_step": fine_p["launches"] // max(1, args.steps),
+                     "avg_launch_ms": fine_p["ms"] / max(1, fine_p["launches"]),
+                     "kernel_share_of_step": fine_p["ms"] / (ms_dev * args.steps),
+                     "coarse_dense": {"tflops": (prof[0]["algo_flops"] / (prof[0]["ms"] / 1e3)) / 1e12 if prof[0]["ms"] > 0 else 0.0,
+                                      "share_of_step": prof[0]["ms"] / (ms_dev * args.steps)},
+                     "whole_step_tflops": flop_step / (ms_dev / 1e3) / 1e12},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(args.n_samples, args.n_importance, args.cpu_sample_rays)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

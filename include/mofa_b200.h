@@ -66,7 +66,7 @@ typedef struct mofa_b200_render_args {
   const float* rays;         /* [n_rays, ray_stride] fp32: o(3) d(3) near far viewdir(3)  (render_class.py:176-179) */
   int64_t n_rays;
   int32_t ray_stride;        /* floats per ray row, >= 11 */
-  int32_t n_samples;         /* N_samples   (coarse samples per ray, 2..256) */
+  int32_t n_samples;         /* N_samples   (coarse samples per ray, 2..256; the reference degenerates at 1) */
   int32_t n_importance;      /* N_importance (0 = single pass) */
   int32_t run_fine;          /* myRenderer.is_run_fineNet (render_class.py:52,321) */
   int32_t fine_net;          /* MOFA_NET_FINE, or MOFA_NET_COARSE when network_fine is None (render_class.py:332) */
@@ -142,6 +142,14 @@ int mofa_b200_dense(mofa_b200_ctx* ctx, const void* A0, const void* B0, int K0, 
 
 /* Number of kernels this library has launched on this context since creation (bench accounting). */
 int64_t mofa_b200_launch_count(mofa_b200_ctx* ctx);
+
+/* Measurement aid (bench.py roofline): while enabled, every tensor-core dense launch is bracketed by a
+ * pair of CUDA events recorded on the launch stream.  profile_read synchronises the device and returns,
+ * per network n in {0 coarse, 1 fine}: out6[3n] = summed launch duration (ms), out6[3n+1] = summed
+ * ALGORITHMIC FLOPs of those launches (2 * rows * out_features * in_features of the reference nn.Linear,
+ * latent columns included), out6[3n+2] = launch count; then clears the records. */
+int mofa_b200_profile_enable(mofa_b200_ctx* ctx, int on);
+int mofa_b200_profile_read(mofa_b200_ctx* ctx, double* out6);
 
 #ifdef __cplusplus
 }

@@ -55,6 +55,8 @@ SIGNATURES = {
     "mofa_b200_dense": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                   C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "mofa_b200_launch_count": (C.c_int64, [C.c_void_p]),
+    "mofa_b200_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
+    "mofa_b200_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
 }
 
 _lib = None

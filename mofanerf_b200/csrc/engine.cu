@@ -54,6 +54,7 @@ struct Layer {
   int fold_n = 0;
   int fold_lat = LAT_NONE;
   int BN = 256;
+  int in_ref = 0;                // reference in_features (algorithmic FLOP accounting)
 };
 
 struct Step {
@@ -82,6 +83,11 @@ struct mofa_b200_ctx {
   float* lat[4] = {nullptr, nullptr, nullptr, nullptr};  // device copies of the current latents
   bool latents_set = false;
   int64_t launches = 0;
+  // profiling (bench): CUDA-event pairs around every tensor-core dense launch, on the launch stream
+  bool profiling = false;
+  std::vector<cudaEvent_t> ev;        // pool: 2 per record
+  struct Rec { int net; double flops; };
+  std::vector<Rec> recs;
 };
 
 namespace {
@@ -133,6 +139,7 @@ int build_layer(mofa_b200_ctx* c, Net& net, const LayerSpec& sp, const float* w,
   Layer L;
   L.N = sp.N;
   L.nseg = sp.nseg;
+  L.in_ref = sp.in_total;
   L.BN = (sp.N % 256 == 0) ? 256 : 128;
   if (sp.N % L.BN != 0) return fail("layer width %d is not a multiple of 128", sp.N);
   for (int i = 0; i < sp.nseg; ++i) {
@@ -230,6 +237,7 @@ int max_width(mofa_b200_ctx* c) {
 
 // Runs the MLP program of `net` over the first P_pad rows of the workspace buffers.
 int run_program(mofa_b200_ctx* c, Net& net, const Workspace& ws, int64_t P_rows, uint32_t flags, cudaStream_t s) {
+  const int net_id = static_cast<int>(&net - c->nets);
   const int64_t M = (P_rows + 127) / 128 * 128;
   auto src_ptr = [&](int id) -> __half* { return id == SRC_X0 ? ws.X0 : id == SRC_V ? ws.V : ws.T[id - SRC_T0]; };
   for (const Step& st : net.program) {
@@ -257,7 +265,23 @@ int run_program(mofa_b200_ctx* c, Net& net, const Workspace& ws, int64_t P_rows,
         for (int i = 0; i < L.nseg; ++i)
           if (make_tmap_2d(c, &d.tmA[i], d.A[i], (uint64_t)M, (uint64_t)L.K[i], (uint64_t)L.K[i], 128)) return 1;
         if (make_tmap_2d(c, &d.tmC, d.C, (uint64_t)M, (uint64_t)L.N, (uint64_t)L.N, 128)) return 1;
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if (c->profiling) {
+          const size_t idx = c->recs.size() * 2;
+          while (c->ev.size() < idx + 2) {
+            cudaEvent_t e;
+            CK(cudaEventCreate(&e));
+            c->ev.push_back(e);
+          }
+          e0 = c->ev[idx];
+          e1 = c->ev[idx + 1];
+          CK(cudaEventRecord(e0, s));
+        }
         CK(launch_dense_tc(d, c->num_sms, s));
+        if (c->profiling) {
+          CK(cudaEventRecord(e1, s));
+          c->recs.push_back({net_id, 2.0 * (double)P_rows * (double)L.N * (double)L.in_ref});
+        }
       }
       c->launches++;
     } else if (st.kind == 1) {
@@ -326,11 +350,36 @@ int mofa_b200_destroy(mofa_b200_ctx* c) {
   cudaSetDevice(c->device);
   for (int i = 0; i < 2; ++i) free_net(c->nets[i]);
   for (int i = 1; i < 4; ++i) cudaFree(c->lat[i]);
+  for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
   delete c;
   return 0;
 }
 
 int64_t mofa_b200_launch_count(mofa_b200_ctx* c) { return c ? c->launches : 0; }
+
+int mofa_b200_profile_enable(mofa_b200_ctx* c, int on) {
+  if (!c) return fail("profile_enable: ctx is NULL");
+  c->profiling = on != 0;
+  c->recs.clear();
+  return 0;
+}
+
+int mofa_b200_profile_read(mofa_b200_ctx* c, double* out6) {
+  if (!c || !out6) return fail("profile_read: NULL argument");
+  CK(cudaSetDevice(c->device));
+  CK(cudaDeviceSynchronize());
+  for (int i = 0; i < 6; ++i) out6[i] = 0.0;
+  for (size_t i = 0; i < c->recs.size(); ++i) {
+    float ms = 0.0f;
+    CK(cudaEventElapsedTime(&ms, c->ev[2 * i], c->ev[2 * i + 1]));
+    const int n = c->recs[i].net;
+    out6[3 * n + 0] += ms;
+    out6[3 * n + 1] += c->recs[i].flops;
+    out6[3 * n + 2] += 1.0;
+  }
+  c->recs.clear();
+  return 0;
+}
 
 int mofa_b200_load_weights(mofa_b200_ctx* c, int net_id, int W, int D, const float* const* t, int n_tensors,
                            void* stream) {
@@ -494,7 +543,7 @@ int mofa_b200_render_rays_fwd(mofa_b200_ctx* c, const mofa_b200_render_args* a, 
   const int S_c = a->n_samples, N_i = a->n_importance;
   const bool fine = (N_i > 0) && a->run_fine;
   const int S_f = fine ? S_c + N_i : 0;
-  if (S_c < 1 || S_c > 256) return fail("render_rays_fwd: n_samples=%d out of range [1,256]", S_c);
+  if (S_c < 2 || S_c > 256) return fail("render_rays_fwd: n_samples=%d out of range [2,256]", S_c);
   if (fine && (S_c < 3 || S_f > 256)) return fail("render_rays_fwd: n_samples+n_importance=%d out of range", S_f);
   Net& nc = c->nets[MOFA_NET_COARSE];
   if (!nc.loaded) return fail("render_rays_fwd: coarse network not loaded");
@@ -607,7 +656,7 @@ int mofa_b200_raw2outputs(mofa_b200_ctx* c, const float* raw, const float* z, co
                           const float* noise, int64_t n, int S, int white_bkgd, float* rgb, float* disp, float* acc,
                           float* weights, float* depth, void* stream) {
   if (!c) return fail("raw2outputs: ctx is NULL");
-  if (S < 1 || S > 256) return fail("raw2outputs: S=%d out of range [1,256]", S);
+  if (S < 2 || S > 256) return fail("raw2outputs: S=%d out of range [2,256]", S);
   CK(cudaSetDevice(c->device));
   CK(launch_composite(raw, z, rays_d, d_stride, noise, 0.0f, 0, 0, n, S, white_bkgd, rgb, disp, acc, weights, depth,
                       static_cast<cudaStream_t>(stream)));

@@ -44,8 +44,10 @@ __device__ __forceinline__ float rng_normal(uint64_t seed, uint32_t stream, uint
 __device__ __forceinline__ float linspace01(int i, int steps) {
   if (steps == 1) return 0.0f;
   const float step = __fdiv_rn(1.0f, static_cast<float>(steps - 1));
+  // ATen evaluates the upper half as one fused multiply-subtract (single rounding); verified bit-exact
+  // against torch.linspace on CPU for steps in {32, 40, 64, 128}.
   return (i < steps / 2) ? __fmul_rn(step, static_cast<float>(i))
-                         : __fsub_rn(1.0f, __fmul_rn(step, static_cast<float>(steps - 1 - i)));
+                         : __fmaf_rn(-step, static_cast<float>(steps - 1 - i), 1.0f);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -390,25 +392,21 @@ sample_pdf_merge_kernel(const float* __restrict__ z, const float* __restrict__ w
   float sum = tot;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  float run = 0.0f;
-#pragma unroll
-  for (int j = 0; j < kMaxPer; ++j) {
-    loc[j] = __fdiv_rn(loc[j], sum);                                                             // pdf
-    run += loc[j];
-  }
-  float incl = run;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const float t = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += t;
-  }
-  float pre = incl - run;   // exclusive prefix of this lane's run
-  if (lane == 0) cdf[0] = 0.0f;
+  // pdf into shared memory, then a sequential running sum by one lane: torch.cumsum (CPU) is a
+  // sequential fp32 scan, and searchsorted decisions at u == cdf[k] depend on its exact rounding.
 #pragma unroll
   for (int j = 0; j < kMaxPer; ++j) {
     const int i = lane * per + j;
-    pre += loc[j];
-    if (j < per && i < nw) cdf[i + 1] = pre;
+    if (j < per && i < nw) cdf[i + 1] = __fdiv_rn(loc[j], sum);                                  // pdf
+  }
+  __syncwarp();
+  if (lane == 0) {
+    cdf[0] = 0.0f;
+    float run = 0.0f;
+    for (int i = 1; i <= nw; ++i) {
+      run = __fadd_rn(run, cdf[i]);
+      cdf[i] = run;
+    }
   }
   __syncwarp();
 

@@ -63,6 +63,15 @@ class Engine:
     def launch_count(self) -> int:
         return int(self.lib.mofa_b200_launch_count(self._h))
 
+    def profile_enable(self, on: bool = True) -> None:
+        _lib.check(self.lib.mofa_b200_profile_enable(self._h, int(on)))
+
+    def profile_read(self) -> dict:
+        """{net: {ms, algo_flops, launches}} for the tensor-core dense launches since the last read."""
+        buf = (C.c_double * 6)()
+        _lib.check(self.lib.mofa_b200_profile_read(self._h, buf))
+        return {n: dict(ms=buf[3 * n], algo_flops=buf[3 * n + 1], launches=int(buf[3 * n + 2])) for n in (0, 1)}
+
     # ------------------------------------------------------------------ weights / latents
     @staticmethod
     def _key(net) -> tuple:
