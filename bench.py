@@ -124,15 +124,32 @@ def measured_peak():
     return 1400.0, "fallback (B200_PROFILING.md: ~1.4 PFLOP/s sustained)"
 
 
+def pick_threads(fn):
+    """Host thread count that runs `fn` fastest among {all, 1/2, 1/4, 1/8 of the logical CPUs} (large boxes are
+    often slower with every SMT thread busy); returns (threads, logical_cpus)."""
+    cores = os.cpu_count() or 1
+    best, best_t = cores, None
+    for th in sorted({cores, max(1, cores // 2), max(1, cores // 4), max(1, cores // 8)}, reverse=True):
+        torch.set_num_threads(th)
+        fn()
+        t0 = time.perf_counter()
+        fn()
+        dt = time.perf_counter() - t0
+        if best_t is None or dt < best_t:
+            best, best_t = th, dt
+    torch.set_num_threads(best)
+    return best, cores
+
+
 def cpu_baseline(n_s, n_i, sample_rays, max_seconds=25.0):
     """The oracle port (fp32 PyTorch restatement of the reference, oracle/mofa_oracle.py) timed on the host
     cores on a bounded sample of the same workload."""
     from oracle import mofa_oracle as O
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     c, f, s = O.build_nets(0)
     shape, tex, exp, ro, rd = synth_inputs(64, 64)
     em = O.expression_mod(s, shape, exp)
+    cal = O.make_ray_batch(ro[:8], rd[:8], 8.0, 26.0)
+    cores, logical = pick_threads(lambda: O.render_rays(cal, c, f, shape, em, tex, N_samples=n_s, N_importance=n_i))
     n = sample_rays if sample_rays > 0 else 64
     best = None
     t_total = 0.0
@@ -149,7 +166,8 @@ def cpu_baseline(n_s, n_i, sample_rays, max_seconds=25.0):
         n = min(4096, int(n * max(2.0, min(8.0, 10.0 / max(dt, 1e-3)))))
     n, dt = best
     return {"value": n / dt, "unit": "rays/s", "cores": cores, "kind": "port",
-            "sample": f"{n} rays x ({n_s} coarse + {n_s + n_i} fine) samples, fp32, oracle/mofa_oracle.py, {dt:.1f} s"}
+            "sample": f"{n} rays x ({n_s} coarse + {n_s + n_i} fine) samples, fp32, oracle/mofa_oracle.py, {dt:.1f} s, "
+                      f"{cores} torch threads (fastest of all/half/quarter/eighth of {logical} logical CPUs)"}
 
 
 def run_reference(args, rank, world):
@@ -158,12 +176,13 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     from oracle import mofa_oracle as O
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     c, f, s = O.build_nets(0)
     shape, tex, exp, ro, rd = synth_inputs(args.H, args.W)
     em = O.expression_mod(s, shape, exp)
-    n = args.cpu_sample_rays if args.cpu_sample_rays > 0 else 256
+    cal = O.make_ray_batch(ro[:8], rd[:8], 8.0, 26.0)
+    cores, logical = pick_threads(lambda: O.render_rays(cal, c, f, shape, em, tex, N_samples=args.n_samples,
+                                                       N_importance=args.n_importance))
+    n = args.cpu_sample_rays if args.cpu_sample_rays > 0 else 128
     idx = torch.linspace(0, ro.shape[0] - 1, n).long()
     rays = O.make_ray_batch(ro[idx], rd[idx], 8.0, 26.0)
     times = []
@@ -174,7 +193,8 @@ def run_reference(args, rank, world):
             times.append(time.perf_counter() - t0)
     ms = 1e3 * sum(times) / len(times)
     val = n / (ms / 1e3)
-    sample = f"{n} rays of the {args.H}x{args.W} frame per step, fp32 PyTorch on {cores} host threads"
+    sample = (f"{n} rays of the {args.H}x{args.W} frame per step, fp32 PyTorch (oracle port), {cores} torch threads "
+              f"(fastest of all/half/quarter/eighth of {logical} logical CPUs)")
     line = {"impl": "reference", "metric": "rays/sec at 800x800x64 samples (FULL: 64 coarse + 128 fine evaluations/ray)",
             "value": val, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",

@@ -57,33 +57,48 @@ def test_raw2outputs_sizes(eng, S):
         assert_close_nan(a.cpu(), b, 2e-5, 2e-5, what=f"S={S}:{nm}")
 
 
-def _check_samples(zs, ref, z, what):
-    """All inverse-CDF samples must match to 1e-4, except the reference's own unstable point: with
-    u == 1.0 (last deterministic sample) the result flips between the last two bin centres depending on
-    whether the fp32 running sum cdf[-1] lands on 1.0 or one ulp above AND the last bin's pdf is below the
-    1e-5 guard (tools/run_nerf_helpers.py:231,243).  torch's own CPU and CUDA cumsum disagree there too;
-    we require that sample to be within one coarse bin."""
+def _check_samples(zs, ref, z, w, u, what):
+    """Inverse-CDF samples vs the oracle, with the tolerance the arithmetic allows.
+
+    sample = bins[b] + (u - cdf[b]) / denom * (bins[a] - bins[b])  (tools/run_nerf_helpers.py:231-245): a
+    one-ulp (6e-8) change of an fp32 cdf entry — e.g. from a different summation order in `sum`/`cumsum`,
+    which already differs between torch's own CPU and CUDA kernels — moves the sample by 6e-8/denom bin
+    widths.  So: |d| <= 1e-4 + 4e-7 / denom * bin_width; where the 1e-5 guard on denom (:243) is itself
+    within rounding of flipping (or u hits cdf[-1] == 1.0), the sample may land anywhere in the two
+    adjacent bins.  Returns the number of guard-ambiguous samples."""
+    bins = 0.5 * (z[:, 1:] + z[:, :-1])
+    ww = w[:, 1:-1] + 1e-5
+    pdf = ww / ww.sum(-1, keepdim=True)
+    cdf = torch.cat([torch.zeros_like(pdf[:, :1]), torch.cumsum(pdf, -1)], -1)
+    inds = torch.searchsorted(cdf, u.contiguous(), right=True)
+    below = (inds - 1).clamp_min(0)
+    above = inds.clamp_max(cdf.shape[-1] - 1)
+    denom = cdf.gather(1, above) - cdf.gather(1, below)
+    width = (bins.gather(1, above) - bins.gather(1, below)).abs()
+    nb_w = (z[:, 1:] - z[:, :-1]).max(-1, keepdim=True)[0]
+    ambiguous = ((denom - 1e-5).abs() < 5e-7) | (u >= cdf[:, -1:] - 2e-7)
+    cond = torch.where(denom < 1e-5, torch.ones_like(denom), denom)
+    tol = 1e-4 + 4e-7 / cond * width
     d = (zs - ref).abs()
-    strict = d[:, :-1]
-    assert strict.max().item() <= 1e-4, f"{what}: max|d|={strict.max().item():.3e}"
-    binw = (z[:, 1:] - z[:, :-1]).max(-1)[0]
-    assert bool((d[:, -1] <= binw + 1e-4).all()), f"{what}: last sample off by more than a bin"
-    return int((d[:, -1] > 1e-4).sum())
+    ok = (d <= tol) | (ambiguous & (d <= 2 * nb_w + 1e-4))
+    assert bool(ok.all()), f"{what}: {int((~ok).sum())} samples out of tolerance, worst {d[~ok].max().item():.3e}"
+    return int(ambiguous.sum())
+
+
+def _linspace_u(n, Ni):
+    return torch.linspace(0.0, 1.0, Ni).expand(n, Ni)
 
 
 def test_sample_pdf_fixture(eng):
     z = T("r2o_z")
     w = T("r2o_wb0_weights")
     zs, zm, sd = eng.sample_pdf_merge(z, w, 64, None)
-    nflip = _check_samples(zs.cpu(), T("pdf_det"), z, "sample_pdf det")
-    if nflip == 0:
-        ref_m = torch.sort(torch.cat([z, T("pdf_det")], -1), -1)[0]
-        assert_close_nan(zm.cpu(), ref_m, 1e-4, what="merged z")
-        assert_close_nan(sd.cpu(), torch.std(T("pdf_det"), dim=-1, unbiased=False), 1e-4, what="z_std")
+    _check_samples(zs.cpu(), T("pdf_det"), z, w, _linspace_u(z.shape[0], 64), "sample_pdf det")
     own = torch.sort(torch.cat([z, zs.cpu()], -1), -1)[0]
     assert torch.equal(zm.cpu(), own), "merge must be the sorted union of coarse depths and samples"
+    assert_close_nan(sd.cpu(), torch.std(zs.cpu(), dim=-1, unbiased=False), 1e-4, what="z_std")
     zs, zm, _ = eng.sample_pdf_merge(z, w, 64, T("pdf_u"))
-    assert_close_nan(zs.cpu(), T("pdf_rand_pytest"), 1e-4, what="sample_pdf explicit u")
+    _check_samples(zs.cpu(), T("pdf_rand_pytest"), z, w, T("pdf_u"), "sample_pdf explicit u")
     assert bool((zm[:, 1:] >= zm[:, :-1]).all()), "merged depths must be sorted"
 
 
@@ -95,7 +110,7 @@ def test_sample_pdf_sizes(eng, S, Ni):
     w = torch.rand(n, S, generator=g) ** 4
     ref = O.sample_pdf(0.5 * (z[:, 1:] + z[:, :-1]), w[:, 1:-1], Ni, det=True)
     zs, zm, sd = eng.sample_pdf_merge(z, w, Ni, None)
-    _check_samples(zs.cpu(), ref, z, "samples")
+    _check_samples(zs.cpu(), ref, z, w, _linspace_u(n, Ni), "samples")
     assert torch.equal(zm.cpu(), torch.sort(torch.cat([z, zs.cpu()], -1), -1)[0])
     assert_close_nan(sd.cpu(), torch.std(zs.cpu(), dim=-1, unbiased=False), 1e-4, what="z_std")
 
