@@ -135,7 +135,8 @@ int mofa_b200_sample_pdf_merge(mofa_b200_ctx* ctx, const float* z, const float* 
 
 /* One dense layer as the engine runs it: C[M,N] = act(A0[M,K0]·B0[N,K0]^T (+ A1[M,K1]·B1[N,K1]^T) + bias).
  * fp16 operands (device, row-major, K0/K1 multiples of 64, N multiple of 128, M multiple of 128),
- * fp32 bias (may be NULL), fp16 output.  use_simt selects the verification kernel. */
+ * fp32 bias (may be NULL), fp16 output.  use_simt: 0 = production kernel (CTA-pair tcgen05 when N % 256 == 0),
+ * 1 = SIMT verification kernel, 2 = single-CTA tcgen05 kernel. */
 int mofa_b200_dense(mofa_b200_ctx* ctx, const void* A0, const void* B0, int K0, const void* A1,
                     const void* B1, int K1, const float* bias, void* C, int64_t M, int N, int relu,
                     int use_simt, void* stream);

@@ -1,0 +1,302 @@
+// Dense layer, CTA-pair version: tcgen05.mma.cta_group::2 on a 256 x 256 output tile per pair of SMs.
+//
+// Same contract as dense_tc.cu (C = act(sum_seg A_seg·B_seg^T + bias), fp16 in / fp32 accumulate / fp16 out)
+// for N % 256 == 0.  Why pairs: with one CTA per 128x256 tile every SM streams the whole 256-row weight
+// block from L2 for its own 128 rows (ncu on the 1-CTA kernel: 6.4 GB L2->SM per 0.55 TFLOP launch,
+// tensor pipe 72-75 % active).  In cta_group::2 mode the two SMs of a TPC hold 128 A-rows each and one
+// HALF of the B tile each; the tensor cores read both halves, so L2->SM bytes per FLOP drop by a third and
+// a stage shrinks to 32 KB per SM (6 stages instead of 4 in the same shared memory).
+//
+// Per CTA (256 threads), cluster of 2:
+//   warp 0 lane 0 : TMA producer — own A half (128x64) + own B half (128x64) per stage, completion bytes
+//                   routed to the LEADER CTA's full barrier (cp.async.bulk.tensor ... .cta_group::2)
+//   warp 1 lane 0 : MMA issuer (leader CTA only) — UMMA 256x256x16, commits multicast to both CTAs
+//   warp 2        : TMEM allocator (cta_group::2, both CTAs)
+//   warps 4..7    : epilogue of this CTA's 128 rows (TMEM -> +bias, ReLU -> fp16 -> swizzled smem -> TMA store);
+//                   one lane per warp releases the accumulator stage on the leader's barrier (remote arrive)
+#include "engine.h"
+#include "ptx.cuh"
+
+namespace mofa {
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `addr` (a shared::cta address in this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_cg2(uint32_t smem_dst, const void* tmap, uint32_t bar_cluster_addr,
+                                                int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_cg2(uint32_t smem_result_addr, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+               ::"r"(smem_result_addr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_cg2() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_cg2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16_ss_cg2(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the barrier at the same shared-memory offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_cg2_mc(uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"(mask)
+      : "memory");
+}
+
+struct Dense2Params {
+  const float* bias;
+  int m_tiles;   // 256-row pair tiles
+  int n_tiles;   // 256-column tiles
+  int kb0, kb1;
+  int relu;
+};
+
+template <int STAGES>
+struct Dense2Smem {
+  static constexpr int A_BYTES = 128 * 64 * 2;
+  static constexpr int B_BYTES = 128 * 64 * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;          // per CTA
+  static constexpr int C_BYTES = 128 * 64 * 2;
+  static constexpr int OFF_C = STAGES * STAGE_BYTES;
+  static constexpr int OFF_BAR = OFF_C + 2 * C_BYTES;
+  static constexpr int N_BARS = 2 * STAGES + 4;
+  static constexpr int OFF_TPTR = OFF_BAR + N_BARS * 8;
+  static constexpr int TOTAL = OFF_TPTR + 16;
+  static constexpr int DYN_BYTES = TOTAL + 1024;
+};
+
+template <int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+dense_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                 const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
+                 const __grid_constant__ CUtensorMap tmC, const Dense2Params p) {
+  using L = Dense2Smem<STAGES>;
+  constexpr int BN = 256;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - raw_addr);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const uint32_t full0 = base + L::OFF_BAR;            // used in the leader only (bytes of both CTAs)
+  const uint32_t empty0 = full0 + 8 * STAGES;          // per CTA
+  const uint32_t tfull0 = empty0 + 8 * STAGES;         // per CTA
+  const uint32_t tempty0 = tfull0 + 16;                // used in the leader only (8 warp arrivals)
+  const uint32_t tptr = base + L::OFF_TPTR;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmA0);
+    prefetch_tmap(&tmB0);
+    prefetch_tmap(&tmC);
+    if (p.kb1 > 0) {
+      prefetch_tmap(&tmA1);
+      prefetch_tmap(&tmB1);
+    }
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(full0 + 8 * i, 1);
+      mbar_init(empty0 + 8 * i, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(tfull0 + 8 * i, 1);
+      mbar_init(tempty0 + 8 * i, 8);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  cluster_sync_all();                                  // barriers of both CTAs initialised before any remote use
+  if (warp == 2) {
+    tmem_alloc_cg2(tptr, 512);
+    tmem_relinquish_cg2();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(base_ptr + L::OFF_TPTR);
+
+  const int num_tiles = p.m_tiles * p.n_tiles;
+  const int total_kb = p.kb0 + p.kb1;
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = pair; t < num_tiles; t += num_pairs) {
+      const int m0 = (t / p.n_tiles) * 256 + static_cast<int>(rank) * 128;
+      const int n0 = (t % p.n_tiles) * BN + static_cast<int>(rank) * 128;
+      for (int kb = 0; kb < total_kb; ++kb) {
+        mbar_wait(empty0 + 8 * stage, phase ^ 1u);
+        const uint32_t fb_local = full0 + 8 * stage;
+        if (leader) mbar_expect_tx(fb_local, 2 * L::STAGE_BYTES);      // bytes of both CTAs land on this barrier
+        const uint32_t fb = mapa_u32(fb_local, 0);
+        const uint32_t sa = base + stage * L::STAGE_BYTES;
+        const uint32_t sb = sa + L::A_BYTES;
+        if (kb < p.kb0) {
+          tma_load_2d_cg2(sa, &tmA0, fb, kb * 64, m0);
+          tma_load_2d_cg2(sb, &tmB0, fb, kb * 64, n0);
+        } else {
+          const int k = (kb - p.kb0) * 64;
+          tma_load_2d_cg2(sa, &tmA1, fb, k, m0);
+          tma_load_2d_cg2(sb, &tmB1, fb, k, n0);
+        }
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0 && leader) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA)
+    constexpr uint32_t idesc = umma_idesc_f16_f32(256, BN);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int t = pair; t < num_tiles; t += num_pairs, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(tempty0 + 8 * as, aphase ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * BN;
+      for (int kb = 0; kb < total_kb; ++kb) {
+        mbar_wait(full0 + 8 * stage, phase);
+        tc_fence_after();
+        const uint32_t sa = base + stage * L::STAGE_BYTES;
+        const uint64_t da = umma_desc_sw128_kmajor(sa);
+        const uint64_t db = umma_desc_sw128_kmajor(sa + L::A_BYTES);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          umma_f16_ss_cg2(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit_cg2_mc(empty0 + 8 * stage, 0x3);   // frees this stage in BOTH CTAs
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+      umma_commit_cg2_mc(tfull0 + 8 * as, 0x3);        // accumulator halves ready in both CTAs
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue (both CTAs, own 128 rows)
+    const int ew = warp - 4;
+    const int ep_tid = threadIdx.x - 128;
+    const int row = ew * 32 + lane;
+    const uint32_t lane_base = static_cast<uint32_t>(ew * 32) << 16;
+    int it = 0;
+    uint32_t cnt = 0;
+    for (int t = pair; t < num_tiles; t += num_pairs, ++it) {
+      const int m0 = (t / p.n_tiles) * 256 + static_cast<int>(rank) * 128;
+      const int n0 = (t % p.n_tiles) * BN;
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(tfull0 + 8 * as, aphase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int cb = 0; cb < BN / 64; ++cb, ++cnt) {
+        const uint32_t cbuf = base + L::OFF_C + (cnt & 1u) * L::C_BYTES;
+        if (ep_tid == 0) tma_store_wait_read<1>();
+        named_bar_sync(1, 128);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tmem_base + lane_base + as * BN + cb * 64 + h * 32, v);
+          tmem_ld_wait();
+          const int ncol = n0 + cb * 64 + h * 32;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              float x = __uint_as_float(v[j * 8 + e]);
+              if (p.bias != nullptr) x += __ldg(p.bias + ncol + j * 8 + e);
+              if (p.relu) x = fmaxf(x, 0.0f);
+              f[e] = fminf(fmaxf(x, -65504.0f), 65504.0f);
+            }
+            __half2 h0 = __floats2half2_rn(f[0], f[1]);
+            __half2 h1 = __floats2half2_rn(f[2], f[3]);
+            __half2 h2 = __floats2half2_rn(f[4], f[5]);
+            __half2 h3 = __floats2half2_rn(f[6], f[7]);
+            const int chunk = h * 4 + j;
+            const uint32_t addr = cbuf + row * 128 + ((chunk ^ (row & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
+                         "r"(*reinterpret_cast<uint32_t*>(&h0)), "r"(*reinterpret_cast<uint32_t*>(&h1)),
+                         "r"(*reinterpret_cast<uint32_t*>(&h2)), "r"(*reinterpret_cast<uint32_t*>(&h3))
+                         : "memory");
+          }
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1, 128);
+        if (ep_tid == 0) {
+          tma_store_2d(&tmC, cbuf, n0 + cb * 64, m0);
+          tma_store_commit();
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(tempty0 + 8 * as, 0));   // 4 warps x 2 CTAs release the stage
+    }
+    if (ep_tid == 0) tma_store_wait_all<0>();
+  }
+  __syncthreads();
+  cluster_sync_all();                                  // peer smem / TMEM stay valid until both CTAs are done
+  if (warp == 2) tmem_dealloc_cg2(tmem_base, 512);
+}
+
+static constexpr int kStages2 = 6;
+
+cudaError_t dense_tc2_configure() {
+  return cudaFuncSetAttribute(dense_tc2_kernel<kStages2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              Dense2Smem<kStages2>::DYN_BYTES);
+}
+
+cudaError_t launch_dense_tc2(const DenseLaunch& L, int num_sms, cudaStream_t stream) {
+  Dense2Params p;
+  p.bias = L.bias;
+  p.m_tiles = static_cast<int>((L.M + 255) / 256);
+  p.n_tiles = L.N / 256;
+  p.kb0 = L.K[0] / 64;
+  p.kb1 = L.K[1] / 64;
+  p.relu = L.relu;
+  const long long tiles = static_cast<long long>(p.m_tiles) * p.n_tiles;
+  if (tiles <= 0) return cudaSuccess;
+  const int max_pairs = num_sms / 2;
+  const int pairs = static_cast<int>(tiles < max_pairs ? tiles : max_pairs);
+  const int s1 = p.kb1 > 0 ? 1 : 0;
+  dense_tc2_kernel<kStages2><<<2 * pairs, 256, Dense2Smem<kStages2>::DYN_BYTES, stream>>>(
+      L.tmA[0], L.tmA[s1], L.tmB2[0], L.tmB2[s1], L.tmC, p);
+  return cudaGetLastError();
+}
+
+}  // namespace mofa

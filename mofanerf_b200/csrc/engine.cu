@@ -4,6 +4,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -47,7 +48,8 @@ struct Layer {
   int nseg = 0;
   int K[2] = {0, 0};             // padded K per segment
   __half* w[2] = {nullptr, nullptr};
-  CUtensorMap tmB[2];
+  CUtensorMap tmB[2];            // box rows = BN (one CTA per tile)
+  CUtensorMap tmB2[2];           // box rows = 128 (CTA-pair kernel: each CTA loads half of the 256 rows)
   float* bias_raw = nullptr;     // [N]
   float* bias_eff = nullptr;     // [N] (== bias_raw when nothing is folded)
   float* fold_w = nullptr;       // [N, fold_n] fp32 latent columns
@@ -82,6 +84,7 @@ struct mofa_b200_ctx {
   Net nets[2];
   float* lat[4] = {nullptr, nullptr, nullptr, nullptr};  // device copies of the current latents
   bool latents_set = false;
+  bool pair_kernel = true;       // cta_group::2 kernel for N % 256 == 0 (MOFA_B200_DENSE_1CTA=1 disables)
   int64_t launches = 0;
   // profiling (bench): CUDA-event pairs around every tensor-core dense launch, on the launch stream
   bool profiling = false;
@@ -148,6 +151,7 @@ int build_layer(mofa_b200_ctx* c, Net& net, const LayerSpec& sp, const float* w,
     CK(launch_pack_weight(w, sp.in_total, sp.seg_c0[i], sp.seg_k[i], L.K[i], sp.N, L.w[i], s));
     c->launches++;
     if (make_tmap_2d(c, &L.tmB[i], L.w[i], sp.N, L.K[i], L.K[i], L.BN)) return 1;
+    if (make_tmap_2d(c, &L.tmB2[i], L.w[i], sp.N, L.K[i], L.K[i], 128)) return 1;
   }
   if (dev_alloc(net, reinterpret_cast<void**>(&L.bias_raw), sizeof(float) * sp.N)) return 1;
   CK(cudaMemcpyAsync(L.bias_raw, b, sizeof(float) * sp.N, cudaMemcpyDeviceToDevice, s));
@@ -251,6 +255,7 @@ int run_program(mofa_b200_ctx* c, Net& net, const Workspace& ws, int64_t P_rows,
         d.K[i] = L.K[i];
         d.lda[i] = L.K[i];   // every source buffer is dense with pitch == its K
         d.tmB[i] = L.tmB[i];
+        d.tmB2[i] = L.tmB2[i];
       }
       d.C = src_ptr(st.out);
       d.ldc = L.N;
@@ -277,7 +282,8 @@ int run_program(mofa_b200_ctx* c, Net& net, const Workspace& ws, int64_t P_rows,
           e1 = c->ev[idx + 1];
           CK(cudaEventRecord(e0, s));
         }
-        CK(launch_dense_tc(d, c->num_sms, s));
+        if (c->pair_kernel && L.BN == 256) CK(launch_dense_tc2(d, c->num_sms, s));
+        else CK(launch_dense_tc(d, c->num_sms, s));
         if (c->profiling) {
           CK(cudaEventRecord(e1, s));
           c->recs.push_back({net_id, 2.0 * (double)P_rows * (double)L.N * (double)L.in_ref});
@@ -329,6 +335,11 @@ int mofa_b200_create(mofa_b200_ctx** out, int device) {
   }
   c->encode = reinterpret_cast<EncodeTiledFn>(fn);
   e = mofa::dense_tc_configure();
+  if (e == cudaSuccess) e = mofa::dense_tc2_configure();
+  {
+    const char* v = getenv("MOFA_B200_DENSE_1CTA");
+    c->pair_kernel = !(v && v[0] == '1');
+  }
   if (e != cudaSuccess) {
     delete c;
     return fail("mofa_b200_create: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
@@ -699,16 +710,18 @@ int mofa_b200_dense(mofa_b200_ctx* c, const void* A0, const void* B0, int K0, co
   d.N = N;
   d.BN = (N % 256 == 0) ? 256 : 128;
   d.relu = relu;
-  if (use_simt) {
+  if (use_simt == 1) {
     CK(launch_dense_simt(d, s));
   } else {
     const int nseg = d.K[1] > 0 ? 2 : 1;
     for (int i = 0; i < nseg; ++i) {
       if (make_tmap_2d(c, &d.tmA[i], d.A[i], (uint64_t)M, (uint64_t)d.K[i], (uint64_t)d.K[i], 128)) return 1;
       if (make_tmap_2d(c, &d.tmB[i], d.B[i], (uint64_t)N, (uint64_t)d.K[i], (uint64_t)d.K[i], d.BN)) return 1;
+      if (make_tmap_2d(c, &d.tmB2[i], d.B[i], (uint64_t)N, (uint64_t)d.K[i], (uint64_t)d.K[i], 128)) return 1;
     }
     if (make_tmap_2d(c, &d.tmC, d.C, (uint64_t)M, (uint64_t)N, (uint64_t)N, 128)) return 1;
-    CK(launch_dense_tc(d, c->num_sms, s));
+    if (use_simt != 2 && c->pair_kernel && d.BN == 256) CK(launch_dense_tc2(d, c->num_sms, s));
+    else CK(launch_dense_tc(d, c->num_sms, s));
   }
   c->launches++;
   return 0;

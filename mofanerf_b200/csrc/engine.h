@@ -11,6 +11,7 @@ namespace mofa {
 struct DenseLaunch {
   CUtensorMap tmA[2];   // activations  [M, K_seg] fp16, box {64, 128}, SWIZZLE_128B
   CUtensorMap tmB[2];   // weights      [N, K_seg] fp16, box {64, BN},  SWIZZLE_128B
+  CUtensorMap tmB2[2];  // weights      [N, K_seg] fp16, box {64, 128}: one CTA's half of a pair tile
   CUtensorMap tmC;      // output       [M, N]     fp16, box {64, 128}, SWIZZLE_128B
   // raw pointers of the same operands (SIMT verification path)
   const __half* A[2];
@@ -29,6 +30,9 @@ struct DenseLaunch {
 cudaError_t launch_dense_tc(const DenseLaunch& L, int num_sms, cudaStream_t stream);
 cudaError_t launch_dense_simt(const DenseLaunch& L, cudaStream_t stream);
 cudaError_t dense_tc_configure();   // one-time cudaFuncSetAttribute for the kernel instantiations
+// CTA-pair (cta_group::2) kernel, N % 256 == 0: 256x256 tile per pair of SMs (dense_tc2.cu)
+cudaError_t launch_dense_tc2(const DenseLaunch& L, int num_sms, cudaStream_t stream);
+cudaError_t dense_tc2_configure();
 
 // ---- element-wise / per-ray kernels (sampling.cu) -----------------------------------------------
 struct RayView {

@@ -37,8 +37,13 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
 // Bounded wait: a protocol bug must trap (visible error) instead of hanging the GPU box.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
+  long long t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) __trap();
+    if ((++spins & 0xFFFu) == 0) {            // every 4096 failed probes: check a ~2 s wall-clock budget
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ll) __trap();
+    }
   }
 }
 

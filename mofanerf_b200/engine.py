@@ -209,8 +209,10 @@ class Engine:
                                                            self._stream()))
         return zs, zm, sd
 
-    def dense(self, A0, B0, bias=None, A1=None, B1=None, relu=True, simt=False):
-        """C = act(A0·B0^T (+ A1·B1^T) + bias) with fp16 operands."""
+    def dense(self, A0, B0, bias=None, A1=None, B1=None, relu=True, simt=False, mode=None):
+        """C = act(A0·B0^T (+ A1·B1^T) + bias) with fp16 operands.
+        mode: None/'default' (CTA-pair tcgen05 when N % 256 == 0), 'simt' (verification), '1cta' (single-CTA tcgen05)."""
+        sel = {None: 1 if simt else 0, 'default': 0, 'simt': 1, '1cta': 2}[mode]
         A0 = A0.to(self.device, torch.float16).contiguous()
         B0 = B0.to(self.device, torch.float16).contiguous()
         M, K0 = A0.shape
@@ -224,7 +226,7 @@ class Engine:
         out = torch.empty(M, N, dtype=torch.float16, device=self.device)
         with torch.cuda.device(self.device):
             _lib.check(self.lib.mofa_b200_dense(self._h, A0.data_ptr(), B0.data_ptr(), K0, _ptr(A1), _ptr(B1), K1,
-                                                _ptr(b), out.data_ptr(), M, N, int(relu), int(simt), self._stream()))
+                                                _ptr(b), out.data_ptr(), M, N, int(relu), sel, self._stream()))
         return out
 
 

@@ -63,7 +63,7 @@ def _check_samples(zs, ref, z, w, u, what):
     sample = bins[b] + (u - cdf[b]) / denom * (bins[a] - bins[b])  (tools/run_nerf_helpers.py:231-245): a
     one-ulp (6e-8) change of an fp32 cdf entry — e.g. from a different summation order in `sum`/`cumsum`,
     which already differs between torch's own CPU and CUDA kernels — moves the sample by 6e-8/denom bin
-    widths.  So: |d| <= 1e-4 + 4e-7 / denom * bin_width; where the 1e-5 guard on denom (:243) is itself
+    widths.  So: |d| <= 1e-4 + 2e-6 / denom * bin_width; where the 1e-5 guard on denom (:243) is itself
     within rounding of flipping (or u hits cdf[-1] == 1.0), the sample may land anywhere in the two
     adjacent bins.  Returns the number of guard-ambiguous samples."""
     bins = 0.5 * (z[:, 1:] + z[:, :-1])
@@ -78,7 +78,7 @@ def _check_samples(zs, ref, z, w, u, what):
     nb_w = (z[:, 1:] - z[:, :-1]).max(-1, keepdim=True)[0]
     ambiguous = ((denom - 1e-5).abs() < 5e-7) | (u >= cdf[:, -1:] - 2e-7)
     cond = torch.where(denom < 1e-5, torch.ones_like(denom), denom)
-    tol = 1e-4 + 4e-7 / cond * width
+    tol = 1e-4 + 2e-6 / cond * width      # 2e-6 ~ worst-case rounding of a 62-term fp32 running sum
     d = (zs - ref).abs()
     ok = (d <= tol) | (ambiguous & (d <= 2 * nb_w + 1e-4))
     assert bool(ok.all()), f"{what}: {int((~ok).sum())} samples out of tolerance, worst {d[~ok].max().item():.3e}"
@@ -124,11 +124,12 @@ def _dense_ref(A0, B0, bias, A1=None, B1=None, relu=True):
     return torch.relu(acc) if relu else acc
 
 
-@pytest.mark.parametrize("M,N,K0,K1", [(128, 256, 64, 0), (256, 128, 64, 0), (384, 256, 256, 0),
+@pytest.mark.parametrize("M,N,K0,K1", [(128, 256, 64, 0), (256, 128, 64, 0), (384, 256, 256, 0), (256, 256, 64, 0),
                                        (1024, 1024, 1024, 0), (640, 256, 256, 256), (512, 512, 64, 1024),
                                        (128 * 301, 1024, 1024, 1024)])
-@pytest.mark.parametrize("simt", [False, True])
-def test_dense_layer(eng, M, N, K0, K1, simt):
+@pytest.mark.parametrize("mode", ["default", "1cta", "simt"])
+def test_dense_layer(eng, M, N, K0, K1, mode):
+    simt = mode == "simt"
     if simt and M > 4096:
         pytest.skip("verification kernel: small shapes only")
     g = torch.Generator().manual_seed(M + N + K0 + K1)
@@ -141,12 +142,12 @@ def test_dense_layer(eng, M, N, K0, K1, simt):
         A1 = (torch.randn(M, K1, generator=g) * 0.5).to(dev)
         B1 = (torch.randn(N, K1, generator=g) * 0.05).to(dev)
     for relu in (True, False):
-        out = eng.dense(A0, B0, bias, A1, B1, relu=relu, simt=simt).float()
+        out = eng.dense(A0, B0, bias, A1, B1, relu=relu, mode=mode).float()
         ref = _dense_ref(A0, B0, bias, A1, B1, relu)
         err = (out - ref).abs()
         lim = 2e-3 * ref.abs() + 2e-3
         bad = int((err > lim).sum())
-        assert bad == 0, (f"dense {'simt' if simt else 'tcgen05'} M={M} N={N} K={K0}+{K1} relu={relu}: {bad} bad, "
+        assert bad == 0, (f"dense {mode} M={M} N={N} K={K0}+{K1} relu={relu}: {bad} bad, "
                           f"max err {err.max().item():.3e}, ref absmax {ref.abs().max().item():.3e}, "
                           f"first bad idx {torch.nonzero(err > lim)[:4].tolist()}")
 

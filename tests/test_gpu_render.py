@@ -70,7 +70,7 @@ def check_maps(name, got, ref, max_rgb=6e-2, mean_rgb=3e-3, min_psnr=40.0, max_a
         if k in ref:
             empty = ref[ka] == 0
             assert bool(torch.isnan(got[k][empty]).all()), f"{name} {k}: NaN expected where acc == 0"
-            solid = ref[ka] > 1e-3
+            solid = (ref[ka] > 1e-3) & (got[ka] > 1e-3)
             if solid.any():
                 rel = ((got[k][solid] - ref[k][solid]).abs() / ref[k][solid].abs().clamp_min(1e-6)).max().item()
                 msgs.append(f"{k}: max rel {rel:.2e}")
