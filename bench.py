@@ -342,7 +342,7 @@ def main():
                 "h2d_bytes_per_step": int(n_loc * 6 * 4), "d2h_bytes_per_step": int(n_total * 3 * 4),
                 "api": "B200Renderer.render_fitting(rays=pinned host tensors) -> rgb copied to pinned host"},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "tensor", "kernel": "dense_tc_kernel<256,4> (fine-net layers, tcgen05 kind::f16)",
+        "roofline": {"bound": "tensor", "kernel": "dense_tc2_kernel<6> (fine-net layers; tcgen05.mma.cta_group::2 kind::f16, 256x256 pair tiles)",
                      "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
                      "peak_source": peak_src, "traffic": traffic,
                      "launches_per_step": fine_p["launches"] // max(1, args.steps),

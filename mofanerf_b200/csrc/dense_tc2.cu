@@ -234,13 +234,19 @@ dense_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           tmem_ld_32x32b_x32(tmem_base + lane_base + as * BN + cb * 64 + h * 32, v);
           tmem_ld_wait();
           const int ncol = n0 + cb * 64 + h * 32;
+          const float4* bias4 = reinterpret_cast<const float4*>(p.bias + ncol);   // 128-byte aligned (ncol % 32 == 0)
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             float f[8];
+            float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+            if (p.bias != nullptr) {
+              b0 = __ldg(bias4 + 2 * j);
+              b1 = __ldg(bias4 + 2 * j + 1);
+            }
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-              float x = __uint_as_float(v[j * 8 + e]);
-              if (p.bias != nullptr) x += __ldg(p.bias + ncol + j * 8 + e);
+              float x = __uint_as_float(v[j * 8 + e]) + bb[e];
               if (p.relu) x = fmaxf(x, 0.0f);
               f[e] = fminf(fmaxf(x, -65504.0f), 65504.0f);
             }

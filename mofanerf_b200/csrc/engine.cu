@@ -282,7 +282,9 @@ int run_program(mofa_b200_ctx* c, Net& net, const Workspace& ws, int64_t P_rows,
           e1 = c->ev[idx + 1];
           CK(cudaEventRecord(e0, s));
         }
-        if (c->pair_kernel && L.BN == 256) CK(launch_dense_tc2(d, c->num_sms, s));
+        // CTA-pair kernel for the wide (fine-net) layers; the narrow coarse layers (N = 256: one n-tile, K = 256)
+        // are epilogue-bound and measured faster on the single-CTA kernel
+        if (c->pair_kernel && L.BN == 256 && L.N >= 512) CK(launch_dense_tc2(d, c->num_sms, s));
         else CK(launch_dense_tc(d, c->num_sms, s));
         if (c->profiling) {
           CK(cudaEventRecord(e1, s));
