@@ -1,0 +1,102 @@
+// Epilogue shared by the single-CTA and CTA-pair dense kernels: one 128-row x BN-column accumulator tile
+//   TMEM --tcgen05.ld--> registers --(+bias, ReLU, clamp)--> fp16 --swizzled st.shared--> TMA store
+// plus the optional fused output head (alpha_linear / rgb_linear, models/model.py:130,134): each thread owns one
+// output row, so the head is a running dot product of the row's activated values with the head weights; the
+// per-tile partial goes to its own slot (row, n_tile) of `head_out` with a plain store — deterministic, no
+// atomics; finalize_raw_kernel adds the slots and the head bias.
+#pragma once
+#include "ptx.cuh"
+
+namespace mofa {
+
+struct EpiParams {
+  const float* bias;      // [N] or nullptr
+  const float* head_w;    // [head_n, N] fp32 or nullptr
+  float* head_out;        // [M, head_stride] fp32 partial slots
+  int relu;
+  int store_c;            // 0: the layer's activations are not needed (view layer with fused rgb head)
+  int head_n;             // 0, 1 or 3
+  int head_stride;        // floats per row in head_out
+  int head_slot0;         // first slot of this head in a row
+  int N;                  // layer width (row pitch of head_w)
+  int M;                  // valid rows of head_out
+};
+
+// acc_addr: TMEM address of this warp's lane quadrant at the accumulator stage's first column.
+// cbuf0: shared address of the two 16 KB staging buffers.  cnt: running staging-buffer counter.
+template <int BN>
+__device__ __forceinline__ void epilogue_tile(const EpiParams& p, const void* tmC, uint32_t acc_addr, uint32_t cbuf0,
+                                              uint32_t& cnt, int m0, int n0, int n_tile, int row, int ep_tid) {
+  float hacc[3] = {0.f, 0.f, 0.f};
+#pragma unroll 1
+  for (int cb = 0; cb < BN / 64; ++cb) {
+    const uint32_t cbuf = cbuf0 + (cnt & 1u) * (128 * 64 * 2);
+    if (p.store_c) {
+      if (ep_tid == 0) tma_store_wait_read<1>();    // the store that last read this buffer is done
+      named_bar_sync(1, 128);
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(acc_addr + cb * 64 + h * 32, v);
+      tmem_ld_wait();
+      const int ncol = n0 + cb * 64 + h * 32;
+      const float4* bias4 = reinterpret_cast<const float4*>(p.bias + ncol);   // 128-byte aligned (ncol % 32 == 0)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float f[8];
+        float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+        if (p.bias != nullptr) {
+          b0 = __ldg(bias4 + 2 * j);
+          b1 = __ldg(bias4 + 2 * j + 1);
+        }
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float x = __uint_as_float(v[j * 8 + e]) + bb[e];
+          if (p.relu) x = fmaxf(x, 0.0f);
+          f[e] = fminf(fmaxf(x, -65504.0f), 65504.0f);
+        }
+        if (p.head_n > 0) {
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            if (q >= p.head_n) break;
+            const float4* w4 = reinterpret_cast<const float4*>(p.head_w + static_cast<size_t>(q) * p.N + ncol) + 2 * j;
+            const float4 w0 = __ldg(w4), w1 = __ldg(w4 + 1);
+            hacc[q] += f[0] * w0.x + f[1] * w0.y + f[2] * w0.z + f[3] * w0.w + f[4] * w1.x + f[5] * w1.y +
+                       f[6] * w1.z + f[7] * w1.w;
+          }
+        }
+        if (p.store_c) {
+          __half2 h0 = __floats2half2_rn(f[0], f[1]);
+          __half2 h1 = __floats2half2_rn(f[2], f[3]);
+          __half2 h2 = __floats2half2_rn(f[4], f[5]);
+          __half2 h3 = __floats2half2_rn(f[6], f[7]);
+          const int chunk = h * 4 + j;              // 16-byte chunk within the 128-byte row
+          const uint32_t addr = cbuf + row * 128 + ((chunk ^ (row & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
+                       "r"(*reinterpret_cast<uint32_t*>(&h0)), "r"(*reinterpret_cast<uint32_t*>(&h1)),
+                       "r"(*reinterpret_cast<uint32_t*>(&h2)), "r"(*reinterpret_cast<uint32_t*>(&h3))
+                       : "memory");
+        }
+      }
+    }
+    if (p.store_c) {
+      fence_proxy_async_smem();
+      named_bar_sync(1, 128);
+      if (ep_tid == 0) {
+        tma_store_2d(tmC, cbuf, n0 + cb * 64, m0);
+        tma_store_commit();
+      }
+      ++cnt;
+    }
+  }
+  if (p.head_n > 0 && m0 + row < p.M) {
+    float* dst = p.head_out + static_cast<size_t>(m0 + row) * p.head_stride + p.head_slot0 + n_tile * p.head_n;
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+      if (q < p.head_n) dst[q] = hacc[q];
+  }
+}
+
+}  // namespace mofa

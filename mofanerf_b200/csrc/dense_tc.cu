@@ -15,18 +15,18 @@
 //   warp 2        : TMEM allocator
 //   warps 4..7    : epilogue      — tcgen05.ld (32 lanes x 32 columns), +bias, ReLU, fp16 pack,
 //                   swizzled st.shared, TMA store; overlaps the next tile's MMAs
+#include "dense_epilogue.cuh"
 #include "engine.h"
 #include "ptx.cuh"
 
 namespace mofa {
 
 struct DenseParams {
-  const float* bias;
+  EpiParams epi;
   int m_tiles;
   int n_tiles;
   int kb0;   // 64-wide K blocks in segment 0
   int kb1;   // ... in segment 1 (0 if none)
-  int relu;
 };
 
 template <int BN, int STAGES>
@@ -164,52 +164,8 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(tfull0 + 8 * as, aphase);
       tc_fence_after();
-#pragma unroll 1
-      for (int cb = 0; cb < BN / 64; ++cb, ++cnt) {
-        const uint32_t cbuf = base + L::OFF_C + (cnt & 1u) * L::C_BYTES;
-        if (ep_tid == 0) tma_store_wait_read<1>();  // the store that last read this buffer is done
-        named_bar_sync(1, 128);
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(tmem_base + lane_base + as * BN + cb * 64 + h * 32, v);
-          tmem_ld_wait();
-          const int ncol = n0 + cb * 64 + h * 32;
-          const float4* bias4 = reinterpret_cast<const float4*>(p.bias + ncol);   // 128-byte aligned (ncol % 32 == 0)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float f[8];
-            float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
-            if (p.bias != nullptr) {
-              b0 = __ldg(bias4 + 2 * j);
-              b1 = __ldg(bias4 + 2 * j + 1);
-            }
-            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              float x = __uint_as_float(v[j * 8 + e]) + bb[e];
-              if (p.relu) x = fmaxf(x, 0.0f);
-              f[e] = fminf(fmaxf(x, -65504.0f), 65504.0f);
-            }
-            __half2 h0 = __floats2half2_rn(f[0], f[1]);
-            __half2 h1 = __floats2half2_rn(f[2], f[3]);
-            __half2 h2 = __floats2half2_rn(f[4], f[5]);
-            __half2 h3 = __floats2half2_rn(f[6], f[7]);
-            const int chunk = h * 4 + j;            // 16-byte chunk within the 128-byte row
-            const uint32_t addr = cbuf + row * 128 + ((chunk ^ (row & 7)) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
-                         "r"(*reinterpret_cast<uint32_t*>(&h0)), "r"(*reinterpret_cast<uint32_t*>(&h1)),
-                         "r"(*reinterpret_cast<uint32_t*>(&h2)), "r"(*reinterpret_cast<uint32_t*>(&h3))
-                         : "memory");
-          }
-        }
-        fence_proxy_async_smem();
-        named_bar_sync(1, 128);
-        if (ep_tid == 0) {
-          tma_store_2d(&tmC, cbuf, n0 + cb * 64, m0);
-          tma_store_commit();
-        }
-      }
+      epilogue_tile<BN>(p.epi, &tmC, tmem_base + lane_base + as * BN, base + L::OFF_C, cnt, m0, n0, t % p.n_tiles, row,
+                        ep_tid);
       tc_fence_before();
       mbar_arrive(tempty0 + 8 * as);                // 128 arrivals release the accumulator stage
     }
@@ -217,6 +173,21 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   }
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+EpiParams make_epi(const DenseLaunch& L) {
+  EpiParams e;
+  e.bias = L.bias;
+  e.head_w = L.head_w;
+  e.head_out = L.head_out;
+  e.relu = L.relu;
+  e.store_c = L.store_c;
+  e.head_n = L.head_w ? L.head_n : 0;
+  e.head_stride = L.head_stride;
+  e.head_slot0 = L.head_slot0;
+  e.N = L.N;
+  e.M = static_cast<int>(L.M);
+  return e;
 }
 
 static constexpr int kStages256 = 4;
@@ -233,12 +204,11 @@ cudaError_t dense_tc_configure() {
 
 cudaError_t launch_dense_tc(const DenseLaunch& L, int num_sms, cudaStream_t stream) {
   DenseParams p;
-  p.bias = L.bias;
+  p.epi = make_epi(L);
   p.m_tiles = static_cast<int>(L.M / 128);
   p.n_tiles = L.N / L.BN;
   p.kb0 = L.K[0] / 64;
   p.kb1 = L.K[1] / 64;
-  p.relu = L.relu;
   const long long tiles = static_cast<long long>(p.m_tiles) * p.n_tiles;
   if (tiles <= 0) return cudaSuccess;
   const int grid = static_cast<int>(tiles < num_sms ? tiles : num_sms);

@@ -14,6 +14,7 @@
 //   warp 2        : TMEM allocator (cta_group::2, both CTAs)
 //   warps 4..7    : epilogue of this CTA's 128 rows (TMEM -> +bias, ReLU -> fp16 -> swizzled smem -> TMA store);
 //                   one lane per warp releases the accumulator stage on the leader's barrier (remote arrive)
+#include "dense_epilogue.cuh"
 #include "engine.h"
 #include "ptx.cuh"
 
@@ -73,11 +74,10 @@ __device__ __forceinline__ void umma_commit_cg2_mc(uint32_t bar, uint16_t mask) 
 }
 
 struct Dense2Params {
-  const float* bias;
+  EpiParams epi;
   int m_tiles;   // 256-row pair tiles
   int n_tiles;   // 256-column tiles
   int kb0, kb1;
-  int relu;
 };
 
 template <int STAGES>
@@ -223,52 +223,8 @@ dense_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(tfull0 + 8 * as, aphase);
       tc_fence_after();
-#pragma unroll 1
-      for (int cb = 0; cb < BN / 64; ++cb, ++cnt) {
-        const uint32_t cbuf = base + L::OFF_C + (cnt & 1u) * L::C_BYTES;
-        if (ep_tid == 0) tma_store_wait_read<1>();
-        named_bar_sync(1, 128);
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(tmem_base + lane_base + as * BN + cb * 64 + h * 32, v);
-          tmem_ld_wait();
-          const int ncol = n0 + cb * 64 + h * 32;
-          const float4* bias4 = reinterpret_cast<const float4*>(p.bias + ncol);   // 128-byte aligned (ncol % 32 == 0)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float f[8];
-            float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
-            if (p.bias != nullptr) {
-              b0 = __ldg(bias4 + 2 * j);
-              b1 = __ldg(bias4 + 2 * j + 1);
-            }
-            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              float x = __uint_as_float(v[j * 8 + e]) + bb[e];
-              if (p.relu) x = fmaxf(x, 0.0f);
-              f[e] = fminf(fmaxf(x, -65504.0f), 65504.0f);
-            }
-            __half2 h0 = __floats2half2_rn(f[0], f[1]);
-            __half2 h1 = __floats2half2_rn(f[2], f[3]);
-            __half2 h2 = __floats2half2_rn(f[4], f[5]);
-            __half2 h3 = __floats2half2_rn(f[6], f[7]);
-            const int chunk = h * 4 + j;
-            const uint32_t addr = cbuf + row * 128 + ((chunk ^ (row & 7)) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
-                         "r"(*reinterpret_cast<uint32_t*>(&h0)), "r"(*reinterpret_cast<uint32_t*>(&h1)),
-                         "r"(*reinterpret_cast<uint32_t*>(&h2)), "r"(*reinterpret_cast<uint32_t*>(&h3))
-                         : "memory");
-          }
-        }
-        fence_proxy_async_smem();
-        named_bar_sync(1, 128);
-        if (ep_tid == 0) {
-          tma_store_2d(&tmC, cbuf, n0 + cb * 64, m0);
-          tma_store_commit();
-        }
-      }
+      epilogue_tile<BN>(p.epi, &tmC, tmem_base + lane_base + as * BN, base + L::OFF_C, cnt, m0, n0, t % p.n_tiles, row,
+                        ep_tid);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_u32(tempty0 + 8 * as, 0));   // 4 warps x 2 CTAs release the stage
@@ -280,6 +236,8 @@ dense_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   if (warp == 2) tmem_dealloc_cg2(tmem_base, 512);
 }
 
+EpiParams make_epi(const DenseLaunch& L);   // dense_tc.cu
+
 static constexpr int kStages2 = 6;
 
 cudaError_t dense_tc2_configure() {
@@ -289,12 +247,11 @@ cudaError_t dense_tc2_configure() {
 
 cudaError_t launch_dense_tc2(const DenseLaunch& L, int num_sms, cudaStream_t stream) {
   Dense2Params p;
-  p.bias = L.bias;
+  p.epi = make_epi(L);
   p.m_tiles = static_cast<int>((L.M + 255) / 256);
   p.n_tiles = L.N / 256;
   p.kb0 = L.K[0] / 64;
   p.kb1 = L.K[1] / 64;
-  p.relu = L.relu;
   const long long tiles = static_cast<long long>(p.m_tiles) * p.n_tiles;
   if (tiles <= 0) return cudaSuccess;
   const int max_pairs = num_sms / 2;

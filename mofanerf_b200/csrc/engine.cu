@@ -35,6 +35,7 @@ int fail(const char* fmt, ...) {
 constexpr int kNShape = 50, kNExp = 30, kNTex = 256, kMultires = 10, kMultiresViews = 4;
 constexpr int kPeXyz = 3 + 6 * kMultires;        // 63
 constexpr int kPeView = 3 + 6 * kMultiresViews;  // 27
+constexpr int kHeadStride = 16;                  // fp32 partial-head slots per point: alpha tiles at 0..3, rgb at 4..15
 
 using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -64,6 +65,7 @@ struct Step {
   int layer;      // index into Net::layers (dense)
   int in[2];      // Src ids
   int out;        // Src id (dense)
+  int head;       // dense step whose output feeds a head: 1 alpha_linear, 2 rgb_linear (fused in the epilogue)
 };
 
 struct Net {
@@ -189,6 +191,7 @@ struct ProgBuilder {
     st.in[0] = in0;
     st.in[1] = in1;
     st.out = free_buf(in0, in1);
+    st.head = 0;
     net.program.push_back(st);
     cur = st.out;
   }
@@ -204,7 +207,7 @@ int fold_net(mofa_b200_ctx* c, Net& net, cudaStream_t s) {
 }
 
 struct Workspace {
-  float *z_c, *w_c, *z_f, *raw;
+  float *z_c, *w_c, *z_f, *raw, *hp;
   __half *X0, *V, *T[3];
   int64_t P_pad;
   size_t total;
@@ -225,6 +228,7 @@ Workspace carve(void* base, int64_t n_chunk, int S_c, int S_f, int Wmax) {
   w.w_c = reinterpret_cast<float*>(b + take(sizeof(float) * n_chunk * S_c));
   w.z_f = reinterpret_cast<float*>(b + take(sizeof(float) * n_chunk * (S_f > 0 ? S_f : 1)));
   w.raw = reinterpret_cast<float*>(b + take(sizeof(float) * 4 * w.P_pad));
+  w.hp = reinterpret_cast<float*>(b + take(sizeof(float) * kHeadStride * w.P_pad));
   w.X0 = reinterpret_cast<__half*>(b + take(sizeof(__half) * 64 * w.P_pad));
   w.V = reinterpret_cast<__half*>(b + take(sizeof(__half) * 64 * w.P_pad));
   for (int i = 0; i < 3; ++i) w.T[i] = reinterpret_cast<__half*>(b + take(sizeof(__half) * (size_t)Wmax * w.P_pad));
@@ -244,6 +248,12 @@ int run_program(mofa_b200_ctx* c, Net& net, const Workspace& ws, int64_t P_rows,
   const int net_id = static_cast<int>(&net - c->nets);
   const int64_t M = (P_rows + 127) / 128 * 128;
   auto src_ptr = [&](int id) -> __half* { return id == SRC_X0 ? ws.X0 : id == SRC_V ? ws.V : ws.T[id - SRC_T0]; };
+  const bool tc = !(flags & MOFA_FLAG_GEMM_SIMT);
+  // head fusion needs every partial slot to fit: W/256 alpha tiles (<= 4), (W/2)/BN rgb tiles (<= 4)
+  const int a_tiles = net.W / 256;
+  const int r_bn = ((net.W / 2) % 256 == 0) ? 256 : 128;
+  const int r_tiles = (net.W / 2) / r_bn;
+  const bool fuse_heads = tc && a_tiles <= 4 && r_tiles <= 4;
   for (const Step& st : net.program) {
     if (st.kind == 0) {
       const Layer& L = net.layers[st.layer];
@@ -264,7 +274,14 @@ int run_program(mofa_b200_ctx* c, Net& net, const Workspace& ws, int64_t P_rows,
       d.N = L.N;
       d.BN = L.BN;
       d.relu = 1;
-      if (flags & MOFA_FLAG_GEMM_SIMT) {
+      d.store_c = 1;
+      if (fuse_heads && st.head == 1) {
+        d.head_w = net.w_alpha; d.head_out = ws.hp; d.head_n = 1; d.head_stride = kHeadStride; d.head_slot0 = 0;
+      } else if (fuse_heads && st.head == 2) {
+        d.head_w = net.w_rgb; d.head_out = ws.hp; d.head_n = 3; d.head_stride = kHeadStride; d.head_slot0 = 4;
+        d.store_c = 0;
+      }
+      if (!tc) {
         CK(launch_dense_simt(d, s));
       } else {
         for (int i = 0; i < L.nseg; ++i)
@@ -292,6 +309,8 @@ int run_program(mofa_b200_ctx* c, Net& net, const Workspace& ws, int64_t P_rows,
         }
       }
       c->launches++;
+    } else if (fuse_heads) {
+      continue;   // computed in the producing layer's epilogue
     } else if (st.kind == 1) {
       CK(launch_head(src_ptr(st.in[0]), net.W, net.w_alpha, net.b_alpha, 1, ws.raw, 3, P_rows, s));
       c->launches++;
@@ -299,6 +318,10 @@ int run_program(mofa_b200_ctx* c, Net& net, const Workspace& ws, int64_t P_rows,
       CK(launch_head(src_ptr(st.in[0]), net.W / 2, net.w_rgb, net.b_rgb, 3, ws.raw, 0, P_rows, s));
       c->launches++;
     }
+  }
+  if (fuse_heads) {
+    CK(launch_finalize_raw(ws.hp, kHeadStride, 0, a_tiles, 4, r_tiles, net.b_alpha, net.b_rgb, ws.raw, P_rows, s));
+    c->launches++;
   }
   return 0;
 }
@@ -479,7 +502,8 @@ int mofa_b200_load_weights(mofa_b200_ctx* c, int net_id, int W, int D, const flo
       }
     }
     if (blk == 0) {   // alpha = alpha_linear(sigmaCodes)   (model.py:130)
-      Step st{1, -1, {pb.cur, -1}, -1};
+      net.program.back().head = 1;
+      Step st{1, -1, {pb.cur, -1}, -1, 0};
       net.program.push_back(st);
     }
   }
@@ -507,7 +531,12 @@ int mofa_b200_load_weights(mofa_b200_ctx* c, int net_id, int W, int D, const flo
   CK(cudaMemcpyAsync(net.w_rgb, w, sizeof(float) * 3 * (W / 2), cudaMemcpyDeviceToDevice, s));
   CK(cudaMemcpyAsync(net.b_rgb, b, sizeof(float) * 3, cudaMemcpyDeviceToDevice, s));
   {
-    Step st{2, -1, {pb.cur, -1}, -1};
+    for (auto it = net.program.rbegin(); it != net.program.rend(); ++it)
+      if (it->kind == 0) {
+        it->head = 2;   // the view layer feeds rgb_linear only
+        break;
+      }
+    Step st{2, -1, {pb.cur, -1}, -1, 0};
     net.program.push_back(st);
   }
   net.loaded = true;
@@ -712,6 +741,7 @@ int mofa_b200_dense(mofa_b200_ctx* c, const void* A0, const void* B0, int K0, co
   d.N = N;
   d.BN = (N % 256 == 0) ? 256 : 128;
   d.relu = relu;
+  d.store_c = 1;
   if (use_simt == 1) {
     CK(launch_dense_simt(d, s));
   } else {

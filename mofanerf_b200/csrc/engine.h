@@ -25,6 +25,12 @@ struct DenseLaunch {
   int N;                // multiple of BN
   int BN;               // 128 or 256
   int relu;
+  // fused output head (tensor-core kernels only): partial dot products of the activated tile rows with
+  // head_w [head_n, N] go to head_out[row * head_stride + head_slot0 + n_tile * head_n + q]
+  const float* head_w;
+  float* head_out;
+  int head_n, head_stride, head_slot0;
+  int store_c;          // 0: do not write C (only the head consumes this layer)
 };
 
 cudaError_t launch_dense_tc(const DenseLaunch& L, int num_sms, cudaStream_t stream);
@@ -67,5 +73,8 @@ cudaError_t launch_pack_weight(const float* src, int ld, int c0, int k, int kpad
 cudaError_t launch_fold_bias(const float* Wsrc, int ld, int c0, int nlat, const float* b, const float* lat,
                              int nrows, float* out, cudaStream_t s);
 cudaError_t launch_copy_f32(const float* src, float* dst, int64_t n, cudaStream_t s);
+// raw[p] = (b_rgb[0..2] + sum of rgb partial slots, b_alpha + sum of alpha partial slots)
+cudaError_t launch_finalize_raw(const float* hp, int stride, int a_slot0, int a_tiles, int r_slot0, int r_tiles,
+                                const float* b_alpha, const float* b_rgb, float* raw, int64_t P, cudaStream_t s);
 
 }  // namespace mofa

@@ -527,4 +527,28 @@ cudaError_t launch_copy_f32(const float* src, float* dst, int64_t n, cudaStream_
   return cudaGetLastError();
 }
 
+__global__ void finalize_raw_kernel(const float* __restrict__ hp, int stride, int a_slot0, int a_tiles, int r_slot0,
+                                    int r_tiles, const float* __restrict__ b_alpha, const float* __restrict__ b_rgb,
+                                    float* __restrict__ raw, int64_t P) {
+  const int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const float* h = hp + p * stride;
+  float a = 0.f, r = 0.f, g = 0.f, b = 0.f;
+  for (int t = 0; t < a_tiles; ++t) a += h[a_slot0 + t];          // fixed order: deterministic
+  for (int t = 0; t < r_tiles; ++t) {
+    r += h[r_slot0 + 3 * t + 0];
+    g += h[r_slot0 + 3 * t + 1];
+    b += h[r_slot0 + 3 * t + 2];
+  }
+  reinterpret_cast<float4*>(raw)[p] = make_float4(r + b_rgb[0], g + b_rgb[1], b + b_rgb[2], a + b_alpha[0]);
+}
+
+cudaError_t launch_finalize_raw(const float* hp, int stride, int a_slot0, int a_tiles, int r_slot0, int r_tiles,
+                                const float* b_alpha, const float* b_rgb, float* raw, int64_t P, cudaStream_t s) {
+  if (P == 0) return cudaSuccess;
+  finalize_raw_kernel<<<static_cast<unsigned>((P + 255) / 256), 256, 0, s>>>(hp, stride, a_slot0, a_tiles, r_slot0,
+                                                                            r_tiles, b_alpha, b_rgb, raw, P);
+  return cudaGetLastError();
+}
+
 }  // namespace mofa
