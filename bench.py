@@ -147,9 +147,13 @@ def cpu_baseline(n_s, n_i, sample_rays, max_seconds=25.0):
     from oracle import mofa_oracle as O
     c, f, s = O.build_nets(0)
     shape, tex, exp, ro, rd = synth_inputs(64, 64)
-    em = O.expression_mod(s, shape, exp)
+    with torch.no_grad():
+        em = O.expression_mod(s, shape, exp)
     cal = O.make_ray_batch(ro[:8], rd[:8], 8.0, 26.0)
-    cores, logical = pick_threads(lambda: O.render_rays(cal, c, f, shape, em, tex, N_samples=n_s, N_importance=n_i))
+    def _cal():
+        with torch.no_grad():
+            O.render_rays(cal, c, f, shape, em, tex, N_samples=n_s, N_importance=n_i)
+    cores, logical = pick_threads(_cal)
     n = sample_rays if sample_rays > 0 else 64
     best = None
     t_total = 0.0
@@ -157,7 +161,8 @@ def cpu_baseline(n_s, n_i, sample_rays, max_seconds=25.0):
         idx = torch.linspace(0, ro.shape[0] - 1, n).long()
         rays = O.make_ray_batch(ro[idx], rd[idx], 8.0, 26.0)
         t0 = time.perf_counter()
-        O.render_rays(rays, c, f, shape, em, tex, N_samples=n_s, N_importance=n_i)
+        with torch.no_grad():
+            O.render_rays(rays, c, f, shape, em, tex, N_samples=n_s, N_importance=n_i)
         dt = time.perf_counter() - t0
         t_total += dt
         best = (n, dt)
@@ -178,17 +183,21 @@ def run_reference(args, rank, world):
     from oracle import mofa_oracle as O
     c, f, s = O.build_nets(0)
     shape, tex, exp, ro, rd = synth_inputs(args.H, args.W)
-    em = O.expression_mod(s, shape, exp)
+    with torch.no_grad():
+        em = O.expression_mod(s, shape, exp)
     cal = O.make_ray_batch(ro[:8], rd[:8], 8.0, 26.0)
-    cores, logical = pick_threads(lambda: O.render_rays(cal, c, f, shape, em, tex, N_samples=args.n_samples,
-                                                       N_importance=args.n_importance))
+    def _cal():
+        with torch.no_grad():
+            O.render_rays(cal, c, f, shape, em, tex, N_samples=args.n_samples, N_importance=args.n_importance)
+    cores, logical = pick_threads(_cal)
     n = args.cpu_sample_rays if args.cpu_sample_rays > 0 else 128
     idx = torch.linspace(0, ro.shape[0] - 1, n).long()
     rays = O.make_ray_batch(ro[idx], rd[idx], 8.0, 26.0)
     times = []
     for i in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        O.render_rays(rays, c, f, shape, em, tex, N_samples=args.n_samples, N_importance=args.n_importance)
+        with torch.no_grad():
+            O.render_rays(rays, c, f, shape, em, tex, N_samples=args.n_samples, N_importance=args.n_importance)
         if i >= args.warmup:
             times.append(time.perf_counter() - t0)
     ms = 1e3 * sum(times) / len(times)

@@ -114,6 +114,45 @@ int mofa_b200_run_network(mofa_b200_ctx* ctx, int net, const float* pts, const f
                           int64_t n_pts, float* raw_out, uint32_t flags, void* workspace,
                           size_t workspace_bytes, void* stream);
 
+/* ---- fitting: forward that keeps activations + backward (run_fit.py:305-313) ----
+ * Differentiable inputs: ray origins / directions / view directions and the three latent codes; network
+ * weights are constants (run_fit.py optimises pose and codes only).  d(disp) is not propagated.
+ * The whole ray batch is one pass (no chunking): the train workspace holds every layer's activation. */
+size_t mofa_b200_train_workspace_bytes(mofa_b200_ctx* ctx, int64_t n_rays, int n_samples, int n_importance,
+                                       int fine_net);
+/* Same arguments and outputs as mofa_b200_render_rays_fwd; args->workspace must be a train workspace and must
+ * be passed unchanged to mofa_b200_render_rays_bwd. */
+int mofa_b200_render_rays_train_fwd(mofa_b200_ctx* ctx, const mofa_b200_render_args* args, void* stream);
+
+typedef struct mofa_b200_bwd_args {
+  uint32_t struct_size;      /* sizeof(mofa_b200_bwd_args) */
+  uint32_t flags;            /* as in the forward call */
+  const float* rays;         /* the forward call's rays */
+  int64_t n_rays;
+  int32_t ray_stride;
+  int32_t n_samples;
+  int32_t n_importance;
+  int32_t run_fine;
+  int32_t fine_net;
+  int32_t reserved;
+  const float* noise_c;      /* the forward call's explicit sigma noise (or NULL) */
+  const float* noise_f;
+  const float* d_rgb;        /* [n,3] dL/d rgb_map   (NULL = zero) */
+  const float* d_acc;        /* [n]   dL/d acc_map */
+  const float* d_rgb0;       /* [n,3] dL/d rgb0      (coarse maps; only when the fine pass ran) */
+  const float* d_acc0;
+  float loss_scale;          /* power of two applied to the fp16 inter-layer gradients, removed at the outputs */
+  float reserved_f;
+  float* d_rays;             /* [n,11] out: d/d o(3), d(3), 0, 0, viewdir(3) */
+  float* d_shape;            /* [50]  out */
+  float* d_expmod;           /* [30]  out: w.r.t. the modulated expression code passed to set_latents */
+  float* d_tex;              /* [256] out */
+  void* workspace;
+  size_t workspace_bytes;
+} mofa_b200_bwd_args;
+
+int mofa_b200_render_rays_bwd(mofa_b200_ctx* ctx, const mofa_b200_bwd_args* args, void* stream);
+
 /* ---- op-level entry points (each one is also a stage of render_rays_fwd) ---- */
 
 /* Embedder.embed (models/model.py:15-63): x [n,3] fp32 -> out [n, 3+6*multires] fp32. */
@@ -132,6 +171,13 @@ int mofa_b200_raw2outputs(mofa_b200_ctx* ctx, const float* raw, const float* z, 
 int mofa_b200_sample_pdf_merge(mofa_b200_ctx* ctx, const float* z, const float* weights, const float* u,
                                int64_t n, int S, int N_i, float* z_samples, float* z_merged,
                                float* z_std, void* stream);
+
+/* Adjoint of raw2outputs w.r.t. raw and |rays_d| (one stage of mofa_b200_render_rays_bwd).  rays [n, stride>=6]
+ * (direction at +3), d_rgb [n,3] / d_acc [n] upstream gradients (may be NULL), outputs d_raw [n,S,4] and d_rays
+ * [n,11] (only columns 3..5 are written; the buffer is zeroed first). */
+int mofa_b200_raw2outputs_bwd(mofa_b200_ctx* ctx, const float* raw, const float* z, const float* rays, int stride,
+                              const float* noise, const float* d_rgb, const float* d_acc, int64_t n, int S,
+                              int white_bkgd, float* d_raw, float* d_rays, void* stream);
 
 /* One dense layer as the engine runs it: C[M,N] = act(A0[M,K0]·B0[N,K0]^T (+ A1[M,K1]·B1[N,K1]^T) + bias).
  * fp16 operands (device, row-major, K0/K1 multiples of 64, N multiple of 128, M multiple of 128),

@@ -29,6 +29,21 @@ class RenderArgs(C.Structure):
     ]
 
 
+class BwdArgs(C.Structure):
+    """mofa_b200_bwd_args (include/mofa_b200.h)."""
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("flags", C.c_uint32),
+        ("rays", C.c_void_p), ("n_rays", C.c_int64),
+        ("ray_stride", C.c_int32), ("n_samples", C.c_int32), ("n_importance", C.c_int32),
+        ("run_fine", C.c_int32), ("fine_net", C.c_int32), ("reserved", C.c_int32),
+        ("noise_c", C.c_void_p), ("noise_f", C.c_void_p),
+        ("d_rgb", C.c_void_p), ("d_acc", C.c_void_p), ("d_rgb0", C.c_void_p), ("d_acc0", C.c_void_p),
+        ("loss_scale", C.c_float), ("reserved_f", C.c_float),
+        ("d_rays", C.c_void_p), ("d_shape", C.c_void_p), ("d_expmod", C.c_void_p), ("d_tex", C.c_void_p),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+    ]
+
+
 FLAG_LINDISP, FLAG_WHITE_BKGD, FLAG_GEMM_SIMT = 1, 2, 8
 NET_COARSE, NET_FINE = 0, 1
 
@@ -43,6 +58,9 @@ SIGNATURES = {
     "mofa_b200_set_latents": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mofa_b200_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int]),
     "mofa_b200_render_rays_fwd": (C.c_int, [C.c_void_p, C.POINTER(RenderArgs), C.c_void_p]),
+    "mofa_b200_train_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int]),
+    "mofa_b200_render_rays_train_fwd": (C.c_int, [C.c_void_p, C.POINTER(RenderArgs), C.c_void_p]),
+    "mofa_b200_render_rays_bwd": (C.c_int, [C.c_void_p, C.POINTER(BwdArgs), C.c_void_p]),
     "mofa_b200_query_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int64]),
     "mofa_b200_run_network": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                                         C.c_uint32, C.c_void_p, C.c_size_t, C.c_void_p]),
@@ -50,6 +68,8 @@ SIGNATURES = {
     "mofa_b200_raw2outputs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                         C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mofa_b200_raw2outputs_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                            C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mofa_b200_sample_pdf_merge": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
                                              C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mofa_b200_dense": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,

@@ -1,0 +1,50 @@
+"""torch.autograd bridge for fitting (run_fit.py:305-313).
+
+Differentiable: the packed ray batch [N,11] (so pose / ray origins / directions / view directions, through
+whatever PyTorch graph built it), the shape code, the modulated expression code and the texture code.
+Constants: network weights (run_fit.py does not optimise them), sample depths (the reference detaches
+z_samples, models/render_class.py:326).  disp_map / z_std are returned as non-differentiable.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+
+class RenderRaysFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rays, shape, exp_mod, tex, engine, cfg):
+        engine.set_latents(shape, exp_mod, tex)
+        out = engine.render_rays(rays.detach(), cfg["N_samples"], cfg["N_importance"], run_fine=cfg["run_fine"],
+                                 fine_net=cfg["fine_net"], perturb=cfg["perturb"], raw_noise_std=cfg["raw_noise_std"],
+                                 lindisp=cfg["lindisp"], white_bkgd=cfg["white_bkgd"], retraw=cfg["retraw"],
+                                 seed=cfg["seed"], t_rand=cfg.get("t_rand"), u=cfg.get("u"), noise_c=cfg.get("noise_c"),
+                                 noise_f=cfg.get("noise_f"), want_aux=cfg.get("want_aux", False), train=True)
+        if cfg["raw_noise_std"] > 0 and cfg.get("noise_c") is None:
+            raise NotImplementedError("training-mode render with in-kernel sigma noise: pass explicit noise tensors")
+        ctx.engine, ctx.cfg = engine, cfg
+        ctx.saved = {k: out.pop(k) for k in ("_train_ws", "_rays", "_noise")}
+        ctx.fine = "rgb0" in out
+        keys = ["rgb_map", "acc_map", "disp_map"] + (["rgb0", "acc0", "disp0", "z_std"] if ctx.fine else [])
+        extra = [k for k in out if k not in keys]
+        ctx.keys = keys + extra
+        ctx.mark_non_differentiable(*[out[k] for k in ctx.keys if k not in ("rgb_map", "acc_map", "rgb0", "acc0")])
+        return tuple(out[k] for k in ctx.keys)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        g = dict(zip(ctx.keys, grads))
+        d_rgb, d_acc = g.get("rgb_map"), g.get("acc_map")
+        d_rgb0, d_acc0 = g.get("rgb0"), g.get("acc0")
+        amax = max([float(x.detach().abs().max()) for x in (d_rgb, d_acc, d_rgb0, d_acc0) if x is not None] + [0.0])
+        # power-of-two loss scale: largest upstream gradient -> ~2^6 in the fp16 inter-layer gradients
+        scale = 2.0 ** round(math.log2(64.0 / amax)) if amax > 0 else 1.0
+        scale = min(max(scale, 2.0 ** -20), 2.0 ** 40)
+        cfg = ctx.cfg
+        d_rays, d_shape, d_exp, d_tex = ctx.engine.render_rays_bwd(
+            ctx.saved, cfg["N_samples"], cfg["N_importance"], run_fine=cfg["run_fine"], fine_net=cfg["fine_net"],
+            white_bkgd=cfg["white_bkgd"], lindisp=cfg["lindisp"], d_rgb=d_rgb, d_acc=d_acc,
+            d_rgb0=d_rgb0 if ctx.fine else None, d_acc0=d_acc0 if ctx.fine else None, loss_scale=scale)
+        ctx.saved = None   # release the activation workspace
+        return d_rays, d_shape, d_exp, d_tex, None, None

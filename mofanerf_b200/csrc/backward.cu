@@ -1,0 +1,291 @@
+// Backward pass of the ray-marching path for fitting (run_fit.py:305-313):
+// gradients of the rendered maps w.r.t. ray origins/directions/view directions and the shape / texture /
+// modulated-expression codes.  Network weights are constants here (they are not optimised in run_fit.py).
+//
+//   composite_bwd      d(rgb_map, acc_map) -> d(raw) per sample, d|rays_d|        raw2outputs   render_class.py:440-482
+//   view_head_bwd      d(raw.rgb) -> dZ of the view layer (rgb_linear^T, ReLU')                 model.py:133-134
+//   dense backward     dZ_T = ReLU'(T) ⊙ (Σ_consumers dZ_c · W_c,seg (+ d_alpha ⊗ w_alpha))     dense_tc*.cu, BWD epilogue
+//   colsum + fold_bwd  d(folded bias) -> d(latent code)                                         the per-call fold's adjoint
+//   pe_bwd             d(X0), d(V) -> d(point), d(viewdir) -> per-ray d(o), d(d)                 model.py:15-63, :315
+//
+// Gradients are carried in fp16 between layers multiplied by a caller-chosen power-of-two loss scale
+// (removed in fp32 at the outputs) so that small gradients stay above fp16's subnormal range.
+#include "engine.h"
+
+namespace mofa {
+
+constexpr int kBwdMaxPer = 8;   // S <= 256
+
+__global__ void composite_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
+                                     const float* __restrict__ rays, int stride, const float* __restrict__ noise,
+                                     const float* __restrict__ d_rgb, const float* __restrict__ d_acc, float gscale,
+                                     int64_t n, int S, int white_bkgd, float* __restrict__ d_raw,
+                                     float* __restrict__ d_rays) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= n) return;
+  const int per = (S + 31) / 32;
+  const float* d = rays + r * stride + 3;
+  const float nd = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+  const float* zr = z + r * S;
+  const float4* rr = reinterpret_cast<const float4*>(raw) + r * S;
+  const float gr = d_rgb ? d_rgb[r * 3 + 0] * gscale : 0.f;
+  const float gg = d_rgb ? d_rgb[r * 3 + 1] * gscale : 0.f;
+  const float gb = d_rgb ? d_rgb[r * 3 + 2] * gscale : 0.f;
+  float ga = d_acc ? d_acc[r] * gscale : 0.f;
+  if (white_bkgd) ga -= (gr + gg + gb);                     // rgb_map += 1 - acc_map   (:479-480)
+
+  float alpha[kBwdMaxPer], tt[kBwdMaxPer], sg[kBwdMaxPer], dist[kBwdMaxPer], gw[kBwdMaxPer];
+  float cr[kBwdMaxPer], cg[kBwdMaxPer], cb[kBwdMaxPer];
+  bool act[kBwdMaxPer];
+  float local = 1.0f;
+#pragma unroll
+  for (int j = 0; j < kBwdMaxPer; ++j) {
+    const int i = lane * per + j;
+    alpha[j] = 0.f; tt[j] = 1.f; sg[j] = 0.f; dist[j] = 0.f; gw[j] = 0.f; cr[j] = cg[j] = cb[j] = 0.f; act[j] = false;
+    if (j < per && i < S) {
+      const float4 v = rr[i];
+      const float dz = (i < S - 1) ? (zr[i + 1] - zr[i]) : 1e10f;
+      dist[j] = dz;
+      float s0 = v.w + (noise ? noise[r * S + i] : 0.f);
+      act[j] = s0 > 0.f;
+      sg[j] = fmaxf(s0, 0.f);
+      alpha[j] = 1.0f - expf(-sg[j] * dz * nd);
+      tt[j] = (1.0f - alpha[j]) + 1e-10f;
+      cr[j] = 1.0f / (1.0f + expf(-v.x));
+      cg[j] = 1.0f / (1.0f + expf(-v.y));
+      cb[j] = 1.0f / (1.0f + expf(-v.z));
+      gw[j] = gr * cr[j] + gg * cg[j] + gb * cb[j] + ga;    // dL/dw_i
+      local *= tt[j];
+    }
+  }
+  // exclusive prefix product of tt across lanes -> T at the start of this lane's run
+  float incl = local;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl *= t;
+  }
+  float T0 = __shfl_up_sync(0xffffffffu, incl, 1);
+  if (lane == 0) T0 = 1.0f;
+  // per-sample T and w; lane-local sum of gw*w, then exclusive suffix sum across lanes
+  float Ti[kBwdMaxPer], wi[kBwdMaxPer];
+  float T = T0, lsum = 0.f;
+#pragma unroll
+  for (int j = 0; j < kBwdMaxPer; ++j) {
+    Ti[j] = T;
+    wi[j] = alpha[j] * T;
+    T *= tt[j];
+    lsum += gw[j] * wi[j];
+  }
+  float suf = lsum;                                         // inclusive suffix over lanes
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float t = __shfl_down_sync(0xffffffffu, suf, o);
+    if (lane + o < 32) suf += t;
+  }
+  float after = suf - lsum;                                 // sum over later lanes
+  float dnorm = 0.f;
+  // walk the lane's run back to front: S_i = sum_{j>i} gw_j w_j
+#pragma unroll
+  for (int j = kBwdMaxPer - 1; j >= 0; --j) {
+    const int i = lane * per + j;
+    if (j < per && i < S) {
+      const float dalpha = gw[j] * Ti[j] - after / tt[j];
+      after += gw[j] * wi[j];
+      const float one_m_a = 1.0f - alpha[j];                // = exp(-sigma*delta)
+      const float delta = dist[j] * nd;
+      const float dsig = act[j] ? dalpha * one_m_a * delta : 0.f;
+      dnorm += dalpha * one_m_a * sg[j] * dist[j];
+      float4 o4;
+      o4.x = wi[j] * gr * cr[j] * (1.f - cr[j]);
+      o4.y = wi[j] * gg * cg[j] * (1.f - cg[j]);
+      o4.z = wi[j] * gb * cb[j] * (1.f - cb[j]);
+      o4.w = dsig;
+      reinterpret_cast<float4*>(d_raw)[r * S + i] = o4;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) dnorm += __shfl_xor_sync(0xffffffffu, dnorm, o);
+  if (lane == 0 && d_rays != nullptr) {                     // d|d| -> d(rays_d): += (not scaled down yet)
+    const float inv = nd > 0.f ? 1.0f / nd : 0.f;
+    d_rays[r * 11 + 3] += dnorm * d[0] * inv;
+    d_rays[r * 11 + 4] += dnorm * d[1] * inv;
+    d_rays[r * 11 + 5] += dnorm * d[2] * inv;
+  }
+}
+
+cudaError_t launch_composite_bwd(const float* raw, const float* z, const float* rays, int stride, const float* noise,
+                                 const float* d_rgb, const float* d_acc, float gscale, int64_t n, int S,
+                                 int white_bkgd, float* d_raw, float* d_rays, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  composite_bwd_kernel<<<static_cast<unsigned>((n + 3) / 4), 128, 0, s>>>(raw, z, rays, stride, noise, d_rgb, d_acc,
+                                                                         gscale, n, S, white_bkgd, d_raw, d_rays);
+  return cudaGetLastError();
+}
+
+// dZ_view[p, c] = (HV[p, c] > 0) ? sum_q d_raw[p, q] * W_rgb[q, c] : 0         (8 columns per thread)
+__global__ void view_head_bwd_kernel(const float* __restrict__ d_raw, const float* __restrict__ w_rgb,
+                                     const __half* __restrict__ HV, int Nh, int64_t P, __half* __restrict__ dZ) {
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int cpr = Nh / 8;
+  if (idx >= P * cpr) return;
+  const int64_t p = idx / cpr;
+  const int c0 = static_cast<int>(idx % cpr) * 8;
+  const float4 g = reinterpret_cast<const float4*>(d_raw)[p];
+  const uint4 hv = reinterpret_cast<const uint4*>(HV + p * Nh + c0)[0];
+  const __half* hh = reinterpret_cast<const __half*>(&hv);
+  __align__(16) __half out[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    float v = g.x * w_rgb[c0 + e] + g.y * w_rgb[Nh + c0 + e] + g.z * w_rgb[2 * Nh + c0 + e];
+    if (!(__half2float(hh[e]) > 0.f)) v = 0.f;
+    out[e] = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+  }
+  reinterpret_cast<uint4*>(dZ + p * Nh + c0)[0] = *reinterpret_cast<const uint4*>(out);
+}
+
+cudaError_t launch_view_head_bwd(const float* d_raw, const float* w_rgb, const __half* HV, int Nh, int64_t P,
+                                 __half* dZ, cudaStream_t s) {
+  const int64_t tot = P * (Nh / 8);
+  if (tot == 0) return cudaSuccess;
+  view_head_bwd_kernel<<<static_cast<unsigned>((tot + 255) / 256), 256, 0, s>>>(d_raw, w_rgb, HV, Nh, P, dZ);
+  return cudaGetLastError();
+}
+
+// out[n] += sum_p dZ[p, n]     grid (N/64, row blocks of 2048); block 256 = 64 columns x 4 row phases
+__global__ void colsum_kernel(const __half* __restrict__ dZ, int N, int64_t P, float* __restrict__ out) {
+  __shared__ float red[4][64];
+  const int c = threadIdx.x & 63, ph = threadIdx.x >> 6;
+  const int col = blockIdx.x * 64 + c;
+  const int64_t r0 = static_cast<int64_t>(blockIdx.y) * 2048;
+  const int64_t r1 = (r0 + 2048 < P) ? r0 + 2048 : P;
+  float acc = 0.f;
+  for (int64_t r = r0 + ph; r < r1; r += 4) acc += __half2float(dZ[r * N + col]);
+  red[ph][c] = acc;
+  __syncthreads();
+  if (ph == 0) atomicAdd(out + col, red[0][c] + red[1][c] + red[2][c] + red[3][c]);
+}
+
+cudaError_t launch_colsum(const __half* dZ, int N, int64_t P, float* out, cudaStream_t s) {
+  if (P == 0) return cudaSuccess;
+  dim3 grid(N / 64, static_cast<unsigned>((P + 2047) / 2048));
+  colsum_kernel<<<grid, 256, 0, s>>>(dZ, N, P, out);
+  return cudaGetLastError();
+}
+
+// d_lat[j] += inv_scale * sum_n fold_w[n, j] * d_beff[n]
+__global__ void fold_bwd_kernel(const float* __restrict__ fold_w, int nlat, int N, const float* __restrict__ d_beff,
+                                float inv_scale, float* __restrict__ d_lat) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nlat) return;
+  float acc = 0.f;
+  for (int n = 0; n < N; ++n) acc += fold_w[static_cast<size_t>(n) * nlat + j] * d_beff[n];
+  d_lat[j] += acc * inv_scale;
+}
+
+cudaError_t launch_fold_bwd(const float* fold_w, int nlat, int N, const float* d_beff, float inv_scale, float* d_lat,
+                            cudaStream_t s) {
+  fold_bwd_kernel<<<(nlat + 63) / 64, 64, 0, s>>>(fold_w, nlat, N, d_beff, inv_scale, d_lat);
+  return cudaGetLastError();
+}
+
+// Adjoint of the positional encoding and of pts = o + d*z; one warp per ray.
+// dX0 / dV rows are `ld` halves wide (columns 0..62 / 0..26 are real).
+template <int LX, int LV>
+__global__ void pe_bwd_kernel(const float* __restrict__ rays, int stride, const float* __restrict__ z,
+                              const __half* __restrict__ dX0, const __half* __restrict__ dV, int ld, int64_t n, int S,
+                              float* __restrict__ d_rays) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= n) return;
+  const float* ray = rays + r * stride;
+  float acc[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // d_o(3), d_d(3), d_v(3)
+  for (int i = lane; i < S; i += 32) {
+    const int64_t p = r * S + i;
+    const float zi = z[p];
+    const __half* gx = dX0 + p * ld;
+    const __half* gv = dV + p * ld;
+    float dpt[3], dvv[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float x = __fadd_rn(ray[c], __fmul_rn(ray[3 + c], zi));
+      float g = __half2float(gx[c]);
+#pragma unroll
+      for (int f = 0; f < LX; ++f) {
+        const float fr = static_cast<float>(1 << f);
+        float sn, cs;
+        sincosf(x * fr, &sn, &cs);
+        g += fr * (cs * __half2float(gx[3 + 6 * f + c]) - sn * __half2float(gx[3 + 6 * f + 3 + c]));
+      }
+      dpt[c] = g;
+      const float v = ray[8 + c];
+      float h = __half2float(gv[c]);
+#pragma unroll
+      for (int f = 0; f < LV; ++f) {
+        const float fr = static_cast<float>(1 << f);
+        float sn, cs;
+        sincosf(v * fr, &sn, &cs);
+        h += fr * (cs * __half2float(gv[3 + 6 * f + c]) - sn * __half2float(gv[3 + 6 * f + 3 + c]));
+      }
+      dvv[c] = h;
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      acc[c] += dpt[c];
+      acc[3 + c] += dpt[c] * zi;
+      acc[6 + c] += dvv[c];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+  }
+  if (lane == 0) {
+    float* o = d_rays + r * 11;      // accumulates in loss-scaled units (both passes); unscaled once at the end
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      o[c] += acc[c];
+      o[3 + c] += acc[3 + c];
+      o[8 + c] += acc[6 + c];
+    }
+  }
+}
+
+cudaError_t launch_pe_bwd(const float* rays, int stride, const float* z, const __half* dX0, const __half* dV, int ld,
+                          int64_t n, int S, float* d_rays, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  pe_bwd_kernel<10, 4><<<static_cast<unsigned>((n + 3) / 4), 128, 0, s>>>(rays, stride, z, dX0, dV, ld, n, S, d_rays);
+  return cudaGetLastError();
+}
+
+// dst[k, n] (fp16, [krows_pad, N]) = src[n * ld + c0 + k] for k < K, zero rows above: transposed weight segment,
+// the K-major "B" operand of the backward GEMMs.
+__global__ void pack_weight_t_kernel(const float* __restrict__ src, int ld, int c0, int K, int krows_pad, int N,
+                                     __half* __restrict__ dst) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<int64_t>(krows_pad) * N) return;
+  const int k = static_cast<int>(i / N), n = static_cast<int>(i % N);
+  dst[i] = __float2half_rn(k < K ? src[static_cast<int64_t>(n) * ld + c0 + k] : 0.0f);
+}
+
+cudaError_t launch_pack_weight_t(const float* src, int ld, int c0, int K, int krows_pad, int N, __half* dst,
+                                 cudaStream_t s) {
+  const int64_t tot = static_cast<int64_t>(krows_pad) * N;
+  pack_weight_t_kernel<<<static_cast<unsigned>((tot + 255) / 256), 256, 0, s>>>(src, ld, c0, K, krows_pad, N, dst);
+  return cudaGetLastError();
+}
+
+__global__ void scale_f32_kernel(float* __restrict__ x, float a, int64_t n) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) x[i] *= a;
+}
+
+cudaError_t launch_scale_f32(float* x, float a, int64_t n, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  scale_f32_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(x, a, n);
+  return cudaGetLastError();
+}
+
+}  // namespace mofa

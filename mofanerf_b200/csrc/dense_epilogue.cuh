@@ -20,14 +20,20 @@ struct EpiParams {
   int head_slot0;         // first slot of this head in a row
   int N;                  // layer width (row pitch of head_w)
   int M;                  // valid rows of head_out
+  // backward-pass options: out = mask ⊙ (acc + r1_row[row] * r1_col[col])
+  const __half* mask;     // [M, N] forward activation of the tensor whose gradient this is (ReLU'), or nullptr
+  const float* r1_row;    // per-row factor (element stride r1_stride) of a rank-1 term, or nullptr
+  const float* r1_col;    // [N] per-column factor
+  int r1_stride;
 };
 
 // acc_addr: TMEM address of this warp's lane quadrant at the accumulator stage's first column.
 // cbuf0: shared address of the two 16 KB staging buffers.  cnt: running staging-buffer counter.
-template <int BN>
+template <int BN, bool BWD>
 __device__ __forceinline__ void epilogue_tile(const EpiParams& p, const void* tmC, uint32_t acc_addr, uint32_t cbuf0,
                                               uint32_t& cnt, int m0, int n0, int n_tile, int row, int ep_tid) {
   float hacc[3] = {0.f, 0.f, 0.f};
+  const float r1 = (BWD && p.r1_row != nullptr && m0 + row < p.M) ? p.r1_row[static_cast<size_t>(m0 + row) * p.r1_stride] : 0.0f;
 #pragma unroll 1
   for (int cb = 0; cb < BN / 64; ++cb) {
     const uint32_t cbuf = cbuf0 + (cnt & 1u) * (128 * 64 * 2);
@@ -50,11 +56,22 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& p, const void* tm
           b0 = __ldg(bias4 + 2 * j);
           b1 = __ldg(bias4 + 2 * j + 1);
         }
-        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        if (BWD && p.r1_row != nullptr) {
+          const float4* c4 = reinterpret_cast<const float4*>(p.r1_col + ncol) + 2 * j;
+          const float4 c0 = __ldg(c4), c1 = __ldg(c4 + 1);
+          bb[0] += r1 * c0.x; bb[1] += r1 * c0.y; bb[2] += r1 * c0.z; bb[3] += r1 * c0.w;
+          bb[4] += r1 * c1.x; bb[5] += r1 * c1.y; bb[6] += r1 * c1.z; bb[7] += r1 * c1.w;
+        }
+        uint4 mk = make_uint4(0x3c003c00u, 0x3c003c00u, 0x3c003c00u, 0x3c003c00u);   // fp16 ones: keep everything
+        if (BWD && p.mask != nullptr && m0 + row < p.M)
+          mk = __ldg(reinterpret_cast<const uint4*>(p.mask + static_cast<size_t>(m0 + row) * p.N + ncol) + j);
+        const __half* mh = reinterpret_cast<const __half*>(&mk);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           float x = __uint_as_float(v[j * 8 + e]) + bb[e];
           if (p.relu) x = fmaxf(x, 0.0f);
+          if (BWD && !(__half2float(mh[e]) > 0.0f)) x = 0.0f;
           f[e] = fminf(fmaxf(x, -65504.0f), 65504.0f);
         }
         if (p.head_n > 0) {

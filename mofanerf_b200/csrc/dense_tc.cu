@@ -43,7 +43,7 @@ struct DenseSmem {
   static constexpr int DYN_BYTES = TOTAL + 1024;   // slack for manual 1024-byte alignment
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool BWD>
 __global__ void __launch_bounds__(256, 1)
 dense_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                 const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
@@ -164,7 +164,7 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(tfull0 + 8 * as, aphase);
       tc_fence_after();
-      epilogue_tile<BN>(p.epi, &tmC, tmem_base + lane_base + as * BN, base + L::OFF_C, cnt, m0, n0, t % p.n_tiles, row,
+      epilogue_tile<BN, BWD>(p.epi, &tmC, tmem_base + lane_base + as * BN, base + L::OFF_C, cnt, m0, n0, t % p.n_tiles, row,
                         ep_tid);
       tc_fence_before();
       mbar_arrive(tempty0 + 8 * as);                // 128 arrivals release the accumulator stage
@@ -186,7 +186,11 @@ EpiParams make_epi(const DenseLaunch& L) {
   e.head_stride = L.head_stride;
   e.head_slot0 = L.head_slot0;
   e.N = L.N;
-  e.M = static_cast<int>(L.M);
+  e.M = static_cast<int>(L.M_valid > 0 ? L.M_valid : L.M);
+  e.mask = L.mask;
+  e.r1_row = L.r1_row;
+  e.r1_col = L.r1_col;
+  e.r1_stride = L.r1_stride;
   return e;
 }
 
@@ -194,12 +198,15 @@ static constexpr int kStages256 = 4;
 static constexpr int kStages128 = 4;
 
 cudaError_t dense_tc_configure() {
-  cudaError_t e = cudaFuncSetAttribute(dense_tc_kernel<256, kStages256>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       DenseSmem<256, kStages256>::DYN_BYTES);
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(dense_tc_kernel<128, kStages128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              DenseSmem<128, kStages128>::DYN_BYTES);
+  cudaError_t e = cudaSuccess;
+  auto set = [&](const void* fn, int bytes) {
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  };
+  set(reinterpret_cast<const void*>(dense_tc_kernel<256, kStages256, false>), DenseSmem<256, kStages256>::DYN_BYTES);
+  set(reinterpret_cast<const void*>(dense_tc_kernel<256, kStages256, true>), DenseSmem<256, kStages256>::DYN_BYTES);
+  set(reinterpret_cast<const void*>(dense_tc_kernel<128, kStages128, false>), DenseSmem<128, kStages128>::DYN_BYTES);
+  set(reinterpret_cast<const void*>(dense_tc_kernel<128, kStages128, true>), DenseSmem<128, kStages128>::DYN_BYTES);
+  return e;
 }
 
 cudaError_t launch_dense_tc(const DenseLaunch& L, int num_sms, cudaStream_t stream) {
@@ -213,13 +220,16 @@ cudaError_t launch_dense_tc(const DenseLaunch& L, int num_sms, cudaStream_t stre
   if (tiles <= 0) return cudaSuccess;
   const int grid = static_cast<int>(tiles < num_sms ? tiles : num_sms);
   const int s1 = p.kb1 > 0 ? 1 : 0;
+  const bool bwd = L.mask != nullptr || L.r1_row != nullptr;
+#define MOFA_LAUNCH(BN_, ST_, BW_)                                                                        \
+  dense_tc_kernel<BN_, ST_, BW_><<<grid, 256, DenseSmem<BN_, ST_>::DYN_BYTES, stream>>>(L.tmA[0], L.tmA[s1],  \
+                                                                                        L.tmB[0], L.tmB[s1], L.tmC, p)
   if (L.BN == 256) {
-    dense_tc_kernel<256, kStages256><<<grid, 256, DenseSmem<256, kStages256>::DYN_BYTES, stream>>>(
-        L.tmA[0], L.tmA[s1], L.tmB[0], L.tmB[s1], L.tmC, p);
+    if (bwd) MOFA_LAUNCH(256, kStages256, true); else MOFA_LAUNCH(256, kStages256, false);
   } else {
-    dense_tc_kernel<128, kStages128><<<grid, 256, DenseSmem<128, kStages128>::DYN_BYTES, stream>>>(
-        L.tmA[0], L.tmA[s1], L.tmB[0], L.tmB[s1], L.tmC, p);
+    if (bwd) MOFA_LAUNCH(128, kStages128, true); else MOFA_LAUNCH(128, kStages128, false);
   }
+#undef MOFA_LAUNCH
   return cudaGetLastError();
 }
 

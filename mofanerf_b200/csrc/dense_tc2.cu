@@ -94,7 +94,7 @@ struct Dense2Smem {
   static constexpr int DYN_BYTES = TOTAL + 1024;
 };
 
-template <int STAGES>
+template <int STAGES, bool BWD>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
 dense_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
@@ -223,7 +223,7 @@ dense_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(tfull0 + 8 * as, aphase);
       tc_fence_after();
-      epilogue_tile<BN>(p.epi, &tmC, tmem_base + lane_base + as * BN, base + L::OFF_C, cnt, m0, n0, t % p.n_tiles, row,
+      epilogue_tile<BN, BWD>(p.epi, &tmC, tmem_base + lane_base + as * BN, base + L::OFF_C, cnt, m0, n0, t % p.n_tiles, row,
                         ep_tid);
       tc_fence_before();
       __syncwarp();
@@ -241,7 +241,10 @@ EpiParams make_epi(const DenseLaunch& L);   // dense_tc.cu
 static constexpr int kStages2 = 6;
 
 cudaError_t dense_tc2_configure() {
-  return cudaFuncSetAttribute(dense_tc2_kernel<kStages2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaError_t e = cudaFuncSetAttribute(dense_tc2_kernel<kStages2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       Dense2Smem<kStages2>::DYN_BYTES);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(dense_tc2_kernel<kStages2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               Dense2Smem<kStages2>::DYN_BYTES);
 }
 
@@ -257,8 +260,12 @@ cudaError_t launch_dense_tc2(const DenseLaunch& L, int num_sms, cudaStream_t str
   const int max_pairs = num_sms / 2;
   const int pairs = static_cast<int>(tiles < max_pairs ? tiles : max_pairs);
   const int s1 = p.kb1 > 0 ? 1 : 0;
-  dense_tc2_kernel<kStages2><<<2 * pairs, 256, Dense2Smem<kStages2>::DYN_BYTES, stream>>>(
-      L.tmA[0], L.tmA[s1], L.tmB2[0], L.tmB2[s1], L.tmC, p);
+  if (L.mask != nullptr || L.r1_row != nullptr)
+    dense_tc2_kernel<kStages2, true><<<2 * pairs, 256, Dense2Smem<kStages2>::DYN_BYTES, stream>>>(
+        L.tmA[0], L.tmA[s1], L.tmB2[0], L.tmB2[s1], L.tmC, p);
+  else
+    dense_tc2_kernel<kStages2, false><<<2 * pairs, 256, Dense2Smem<kStages2>::DYN_BYTES, stream>>>(
+        L.tmA[0], L.tmA[s1], L.tmB2[0], L.tmB2[s1], L.tmC, p);
   return cudaGetLastError();
 }
 

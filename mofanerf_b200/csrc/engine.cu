@@ -58,6 +58,13 @@ struct Layer {
   int fold_lat = LAT_NONE;
   int BN = 256;
   int in_ref = 0;                // reference in_features (algorithmic FLOP accounting)
+  // backward: transposed segment weights [rows_t, N] (rows_t = K padded to >= 128), the
+  // K-major B operand of dX = dZ · W
+  __half* wt[2] = {nullptr, nullptr};
+  int rows_t[2] = {0, 0};
+  int BN_t[2] = {256, 256};
+  CUtensorMap tmBt[2];           // box rows = BN_t
+  CUtensorMap tmBt2[2];          // box rows = 128 (CTA-pair kernel)
 };
 
 struct Step {
@@ -66,6 +73,8 @@ struct Step {
   int in[2];      // Src ids
   int out;        // Src id (dense)
   int head;       // dense step whose output feeds a head: 1 alpha_linear, 2 rgb_linear (fused in the epilogue)
+  int in_step[2]; // producer of each input: dense ordinal >= 0, -1 = X0 (point encoding), -2 = V (view encoding), -3 none
+  int ord;        // ordinal among the dense steps
 };
 
 struct Net {
@@ -154,6 +163,13 @@ int build_layer(mofa_b200_ctx* c, Net& net, const LayerSpec& sp, const float* w,
     c->launches++;
     if (make_tmap_2d(c, &L.tmB[i], L.w[i], sp.N, L.K[i], L.K[i], L.BN)) return 1;
     if (make_tmap_2d(c, &L.tmB2[i], L.w[i], sp.N, L.K[i], L.K[i], 128)) return 1;
+    L.rows_t[i] = L.K[i] < 128 ? 128 : L.K[i];
+    L.BN_t[i] = (L.rows_t[i] % 256 == 0) ? 256 : 128;
+    if (dev_alloc(net, reinterpret_cast<void**>(&L.wt[i]), sizeof(__half) * (size_t)L.rows_t[i] * sp.N)) return 1;
+    CK(launch_pack_weight_t(w, sp.in_total, sp.seg_c0[i], sp.seg_k[i], L.rows_t[i], sp.N, L.wt[i], s));
+    c->launches++;
+    if (make_tmap_2d(c, &L.tmBt[i], L.wt[i], L.rows_t[i], sp.N, sp.N, L.BN_t[i])) return 1;
+    if (make_tmap_2d(c, &L.tmBt2[i], L.wt[i], L.rows_t[i], sp.N, sp.N, 128)) return 1;
   }
   if (dev_alloc(net, reinterpret_cast<void**>(&L.bias_raw), sizeof(float) * sp.N)) return 1;
   CK(cudaMemcpyAsync(L.bias_raw, b, sizeof(float) * sp.N, cudaMemcpyDeviceToDevice, s));
@@ -178,6 +194,8 @@ struct ProgBuilder {
   Net& net;
   int cur = SRC_X0;
   int pinned = -1;
+  int writer[SRC_T0 + 3] = {-1, -2, -3, -3, -3};   // last dense ordinal that wrote each buffer (X0 = -1, V = -2)
+  int n_dense = 0;
   explicit ProgBuilder(Net& n) : net(n) {}
   int free_buf(int a, int b) const {
     for (int t = SRC_T0; t < SRC_T0 + 3; ++t)
@@ -192,6 +210,10 @@ struct ProgBuilder {
     st.in[1] = in1;
     st.out = free_buf(in0, in1);
     st.head = 0;
+    st.in_step[0] = writer[in0];
+    st.in_step[1] = in1 >= 0 ? writer[in1] : -3;
+    st.ord = n_dense++;
+    writer[st.out] = st.ord;
     net.program.push_back(st);
     cur = st.out;
   }
@@ -244,7 +266,9 @@ int max_width(mofa_b200_ctx* c) {
 }
 
 // Runs the MLP program of `net` over the first P_pad rows of the workspace buffers.
-int run_program(mofa_b200_ctx* c, Net& net, const Workspace& ws, int64_t P_rows, uint32_t flags, cudaStream_t s) {
+int run_program(mofa_b200_ctx* c, Net& net, const Workspace& ws, int64_t P_rows, uint32_t flags, cudaStream_t s,
+                __half* const* act = nullptr) {
+  // act != nullptr: training mode — dense step k writes act[k] (kept for the backward pass) instead of the ping-pong buffers
   const int net_id = static_cast<int>(&net - c->nets);
   const int64_t M = (P_rows + 127) / 128 * 128;
   auto src_ptr = [&](int id) -> __half* { return id == SRC_X0 ? ws.X0 : id == SRC_V ? ws.V : ws.T[id - SRC_T0]; };
@@ -260,14 +284,14 @@ int run_program(mofa_b200_ctx* c, Net& net, const Workspace& ws, int64_t P_rows,
       DenseLaunch d;
       memset(&d, 0, sizeof(d));
       for (int i = 0; i < L.nseg; ++i) {
-        d.A[i] = src_ptr(st.in[i]);
+        d.A[i] = (act && st.in_step[i] >= 0) ? act[st.in_step[i]] : src_ptr(st.in[i]);
         d.B[i] = L.w[i];
         d.K[i] = L.K[i];
         d.lda[i] = L.K[i];   // every source buffer is dense with pitch == its K
         d.tmB[i] = L.tmB[i];
         d.tmB2[i] = L.tmB2[i];
       }
-      d.C = src_ptr(st.out);
+      d.C = act ? act[st.ord] : src_ptr(st.out);
       d.ldc = L.N;
       d.bias = L.bias_eff;
       d.M = M;
@@ -279,7 +303,7 @@ int run_program(mofa_b200_ctx* c, Net& net, const Workspace& ws, int64_t P_rows,
         d.head_w = net.w_alpha; d.head_out = ws.hp; d.head_n = 1; d.head_stride = kHeadStride; d.head_slot0 = 0;
       } else if (fuse_heads && st.head == 2) {
         d.head_w = net.w_rgb; d.head_out = ws.hp; d.head_n = 3; d.head_stride = kHeadStride; d.head_slot0 = 4;
-        d.store_c = 0;
+        d.store_c = act ? 1 : 0;   // the backward pass needs the view layer's activation (ReLU')
       }
       if (!tc) {
         CK(launch_dense_simt(d, s));
@@ -503,7 +527,7 @@ int mofa_b200_load_weights(mofa_b200_ctx* c, int net_id, int W, int D, const flo
     }
     if (blk == 0) {   // alpha = alpha_linear(sigmaCodes)   (model.py:130)
       net.program.back().head = 1;
-      Step st{1, -1, {pb.cur, -1}, -1, 0};
+      Step st{1, -1, {pb.cur, -1}, -1, 0, {-3, -3}, -1};
       net.program.push_back(st);
     }
   }
@@ -536,7 +560,7 @@ int mofa_b200_load_weights(mofa_b200_ctx* c, int net_id, int W, int D, const flo
         it->head = 2;   // the view layer feeds rgb_linear only
         break;
       }
-    Step st{2, -1, {pb.cur, -1}, -1, 0};
+    Step st{2, -1, {pb.cur, -1}, -1, 0, {-3, -3}, -1};
     net.program.push_back(st);
   }
   net.loaded = true;
@@ -755,6 +779,275 @@ int mofa_b200_dense(mofa_b200_ctx* c, const void* A0, const void* B0, int K0, co
     if (use_simt != 2 && c->pair_kernel && d.BN == 256) CK(launch_dense_tc2(d, c->num_sms, s));
     else CK(launch_dense_tc(d, c->num_sms, s));
   }
+  c->launches++;
+  return 0;
+}
+
+}  // extern "C"
+
+// =================================================================================================
+// fitting: training-mode forward + backward
+// =================================================================================================
+namespace {
+
+struct PassBufs {
+  float *z, *raw;                 // [n,S], [P,4]
+  std::vector<__half*> act;       // per dense step: [P_pad, N]
+};
+
+struct TrainWS {
+  Workspace fw;                   // forward scratch shared by both passes (X0, V, hp, z_c, w_c, z_f, raw)
+  PassBufs pass[2];               // 0 = coarse pass, 1 = fine pass
+  std::vector<__half*> dz;        // backward: per dense step of the widest/deepest net: [P_pad, Wmax]
+  __half *dX0, *dV;               // [P_pad,128]
+  float* d_raw;                   // [P_pad,4]
+  float* d_beff;                  // [Wmax]
+  size_t total;
+};
+
+int n_dense_steps(const Net& n) {
+  int k = 0;
+  for (const Step& s : n.program) k += s.kind == 0;
+  return k;
+}
+
+TrainWS carve_train(void* base, int64_t n, int S_c, int S_f, const Net& nc, const Net* nf) {
+  TrainWS t;
+  const int Wmax = nf && nf->W > nc.W ? nf->W : nc.W;
+  t.fw = carve(base, n, S_c, S_f, Wmax);
+  size_t off = align_up(t.fw.total, 1024);
+  uint8_t* b = static_cast<uint8_t*>(base);
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off = align_up(off + bytes, 1024);
+    return b + o;
+  };
+  const int64_t P_c = (n * S_c + 127) / 128 * 128;
+  const int64_t P_f = (n * (S_f > 0 ? S_f : 1) + 127) / 128 * 128;
+  for (int ps = 0; ps < 2; ++ps) {
+    const Net* net = ps == 0 ? &nc : nf;
+    if (!net) continue;
+    const int64_t P = ps == 0 ? P_c : P_f;
+    const int S = ps == 0 ? S_c : S_f;
+    t.pass[ps].z = reinterpret_cast<float*>(take(sizeof(float) * n * S));
+    t.pass[ps].raw = reinterpret_cast<float*>(take(sizeof(float) * 4 * P));
+    for (const Step& st : net->program)
+      if (st.kind == 0)
+        t.pass[ps].act.push_back(reinterpret_cast<__half*>(take(sizeof(__half) * (size_t)P * net->layers[st.layer].N)));
+  }
+  const int64_t P_max = P_f > P_c && nf ? P_f : P_c;
+  int nd = n_dense_steps(nc);
+  if (nf && n_dense_steps(*nf) > nd) nd = n_dense_steps(*nf);
+  for (int k = 0; k < nd; ++k) t.dz.push_back(reinterpret_cast<__half*>(take(sizeof(__half) * (size_t)P_max * Wmax)));
+  t.dX0 = reinterpret_cast<__half*>(take(sizeof(__half) * (size_t)P_max * 128));
+  t.dV = reinterpret_cast<__half*>(take(sizeof(__half) * (size_t)P_max * 128));
+  t.d_raw = reinterpret_cast<float*>(take(sizeof(float) * 4 * P_max));
+  t.d_beff = reinterpret_cast<float*>(take(sizeof(float) * Wmax));
+  t.total = off;
+  return t;
+}
+
+// Backward of one pass through `net`: d_raw (loss-scaled) -> dX0/dV and latent gradients.
+int run_backward(mofa_b200_ctx* c, Net& net, const TrainWS& t, const PassBufs& pb, int64_t P_rows, float inv_scale,
+                 float* const d_lat[4], cudaStream_t s) {
+  const int64_t M = (P_rows + 127) / 128 * 128;
+  std::vector<const Step*> dense;
+  for (const Step& st : net.program)
+    if (st.kind == 0) dense.push_back(&st);
+  const int nd = static_cast<int>(dense.size());
+  auto gemm = [&](int target /* dense ordinal, -1 X0, -2 V */, int width, __half* out, const __half* mask,
+                  bool rank1) -> int {
+    DenseLaunch d;
+    memset(&d, 0, sizeof(d));
+    int nseg = 0;
+    for (int cidx = 0; cidx < nd && nseg < 2; ++cidx) {
+      const Step& cs = *dense[cidx];
+      const Layer& CL = net.layers[cs.layer];
+      for (int i = 0; i < CL.nseg; ++i) {
+        if (cs.in_step[i] != target) continue;
+        if (nseg == 2) return fail("backward: tensor with more than two consumers");
+        d.A[nseg] = t.dz[cidx];
+        d.B[nseg] = CL.wt[i];
+        d.K[nseg] = CL.N;
+        d.lda[nseg] = CL.N;
+        d.tmB[nseg] = CL.tmBt[i];
+        d.tmB2[nseg] = CL.tmBt2[i];
+        if (CL.rows_t[i] != width) return fail("backward: width mismatch (%d vs %d)", CL.rows_t[i], width);
+        if (make_tmap_2d(c, &d.tmA[nseg], d.A[nseg], (uint64_t)M, (uint64_t)CL.N, (uint64_t)CL.N, 128)) return 1;
+        ++nseg;
+      }
+    }
+    if (nseg == 0) return fail("backward: tensor %d has no consumer", target);
+    d.C = out;
+    d.ldc = width;
+    d.M = M;
+    d.M_valid = M;
+    d.N = width;
+    d.BN = (width % 256 == 0) ? 256 : 128;
+    d.relu = 0;
+    d.store_c = 1;
+    d.mask = mask;
+    if (rank1) {
+      d.r1_row = t.d_raw + 3;
+      d.r1_stride = 4;
+      d.r1_col = net.w_alpha;
+    }
+    if (make_tmap_2d(c, &d.tmC, d.C, (uint64_t)M, (uint64_t)width, (uint64_t)width, 128)) return 1;
+    if (c->pair_kernel && d.BN == 256 && width >= 512) CK(launch_dense_tc2(d, c->num_sms, s));
+    else CK(launch_dense_tc(d, c->num_sms, s));
+    c->launches++;
+    return 0;
+  };
+  for (int k = nd - 1; k >= 0; --k) {
+    const Step& st = *dense[k];
+    const Layer& L = net.layers[st.layer];
+    if (st.head == 2) {   // view layer: only rgb_linear consumes it
+      CK(launch_view_head_bwd(t.d_raw, net.w_rgb, pb.act[k], L.N, P_rows, t.dz[k], s));
+      c->launches++;
+    } else {
+      if (gemm(k, L.N, t.dz[k], pb.act[k], st.head == 1)) return 1;
+    }
+    if (L.fold_n > 0) {   // adjoint of the latent fold: d(bias_eff) = column sums of dZ
+      CK(cudaMemsetAsync(t.d_beff, 0, sizeof(float) * L.N, s));
+      CK(launch_colsum(t.dz[k], L.N, P_rows, t.d_beff, s));
+      CK(launch_fold_bwd(L.fold_w, L.fold_n, L.N, t.d_beff, inv_scale, d_lat[L.fold_lat], s));
+      c->launches += 2;
+    }
+  }
+  if (gemm(-1, 128, t.dX0, nullptr, false)) return 1;
+  if (gemm(-2, 128, t.dV, nullptr, false)) return 1;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t mofa_b200_train_workspace_bytes(mofa_b200_ctx* c, int64_t n_rays, int n_samples, int n_importance, int fine_net) {
+  if (!c || !c->nets[0].loaded) return 0;
+  const bool fine = n_importance > 0;
+  if (fine && (fine_net < 0 || fine_net > 1 || !c->nets[fine_net].loaded)) return 0;
+  return carve_train(nullptr, n_rays, n_samples, fine ? n_samples + n_importance : 0, c->nets[0],
+                     fine ? &c->nets[fine_net] : nullptr).total + 1024;
+}
+
+int mofa_b200_render_rays_train_fwd(mofa_b200_ctx* c, const mofa_b200_render_args* a, void* stream) {
+  if (!c || !a) return fail("train_fwd: NULL argument");
+  if (a->struct_size != sizeof(mofa_b200_render_args)) return fail("train_fwd: struct_size mismatch");
+  if (a->n_rays <= 0) return fail("train_fwd: n_rays must be positive");
+  if (!a->rays || a->ray_stride < 11) return fail("train_fwd: rays NULL or ray_stride < 11");
+  if (a->flags & MOFA_FLAG_GEMM_SIMT) return fail("train_fwd: the SIMT verification kernel has no training mode");
+  const int S_c = a->n_samples, N_i = a->n_importance;
+  const bool fine = (N_i > 0) && a->run_fine;
+  const int S_f = fine ? S_c + N_i : 0;
+  if (S_c < 2 || S_c > 256 || (fine && (S_c < 3 || S_f > 256))) return fail("train_fwd: sample counts out of range");
+  Net& nc = c->nets[0];
+  if (!nc.loaded) return fail("train_fwd: coarse network not loaded");
+  if (fine && (a->fine_net < 0 || a->fine_net > 1 || !c->nets[a->fine_net].loaded))
+    return fail("train_fwd: fine network not loaded");
+  Net* nf = fine ? &c->nets[a->fine_net] : nullptr;
+  if (!c->latents_set) return fail("train_fwd: set_latents has not been called");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!a->workspace) return fail("train_fwd: workspace is NULL");
+  uint8_t* wbase = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<size_t>(a->workspace), 1024));
+  const size_t slack = wbase - static_cast<uint8_t*>(a->workspace);
+  TrainWS t = carve_train(wbase, a->n_rays, S_c, S_f, nc, nf);
+  if (t.total + slack > a->workspace_bytes)
+    return fail("train_fwd: workspace too small (%zu < %zu)", a->workspace_bytes, t.total + slack);
+  const int64_t n = a->n_rays;
+  const int lindisp = (a->flags & MOFA_FLAG_LINDISP) ? 1 : 0;
+  const int white = (a->flags & MOFA_FLAG_WHITE_BKGD) ? 1 : 0;
+  Workspace ws = t.fw;
+  // ---- coarse pass (activations kept)
+  CK(launch_zvals_coarse(a->rays, a->ray_stride, n, S_c, lindisp, a->perturb, a->t_rand, a->seed, 0, t.pass[0].z, s));
+  CK(launch_encode_rays(a->rays, a->ray_stride, t.pass[0].z, n, S_c, kMultires, kMultiresViews, ws.X0, ws.V, s));
+  c->launches += 2;
+  ws.raw = t.pass[0].raw;
+  if (run_program(c, nc, ws, n * S_c, a->flags, s, t.pass[0].act.data())) return 1;
+  CK(launch_composite(ws.raw, t.pass[0].z, a->rays + 3, a->ray_stride, a->noise_c, a->raw_noise_std, a->seed, 0, n,
+                      S_c, white, fine ? a->rgb0 : a->rgb, fine ? a->disp0 : a->disp, fine ? a->acc0 : a->acc, ws.w_c,
+                      nullptr, s));
+  c->launches++;
+  const float* z_last = t.pass[0].z;
+  const float* raw_last = t.pass[0].raw;
+  if (fine) {
+    const int det = (a->perturb == 0.0f) ? 1 : 0;
+    CK(launch_sample_pdf_merge(t.pass[0].z, ws.w_c, a->u, det, a->seed, 0, n, S_c, N_i, nullptr, t.pass[1].z, a->z_std, s));
+    CK(launch_encode_rays(a->rays, a->ray_stride, t.pass[1].z, n, S_f, kMultires, kMultiresViews, ws.X0, ws.V, s));
+    c->launches += 2;
+    ws.raw = t.pass[1].raw;
+    if (run_program(c, *nf, ws, n * S_f, a->flags, s, t.pass[1].act.data())) return 1;
+    CK(launch_composite(ws.raw, t.pass[1].z, a->rays + 3, a->ray_stride, a->noise_f, a->raw_noise_std,
+                        a->seed + 0x9E3779B97F4A7C15ull, 0, n, S_f, white, a->rgb, a->disp, a->acc, a->weights, nullptr,
+                        s));
+    c->launches++;
+    z_last = t.pass[1].z;
+    raw_last = t.pass[1].raw;
+  } else if (a->weights) {
+    CK(launch_copy_f32(ws.w_c, a->weights, n * S_c, s));
+  }
+  const int S_last = fine ? S_f : S_c;
+  if (a->raw) CK(launch_copy_f32(raw_last, a->raw, n * S_last * 4, s));
+  if (a->z_vals) CK(launch_copy_f32(z_last, a->z_vals, n * S_last, s));
+  return 0;
+}
+
+int mofa_b200_render_rays_bwd(mofa_b200_ctx* c, const mofa_b200_bwd_args* a, void* stream) {
+  if (!c || !a) return fail("bwd: NULL argument");
+  if (a->struct_size != sizeof(mofa_b200_bwd_args)) return fail("bwd: struct_size mismatch");
+  if (a->n_rays <= 0 || !a->rays || !a->workspace) return fail("bwd: bad arguments");
+  if (!a->d_rays || !a->d_shape || !a->d_expmod || !a->d_tex) return fail("bwd: output pointers must not be NULL");
+  const int S_c = a->n_samples, N_i = a->n_importance;
+  const bool fine = (N_i > 0) && a->run_fine;
+  const int S_f = fine ? S_c + N_i : 0;
+  Net& nc = c->nets[0];
+  Net* nf = fine ? &c->nets[a->fine_net] : nullptr;
+  if (!nc.loaded || (fine && !nf->loaded)) return fail("bwd: networks not loaded");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  uint8_t* wbase = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<size_t>(a->workspace), 1024));
+  const size_t slack = wbase - static_cast<uint8_t*>(a->workspace);
+  TrainWS t = carve_train(wbase, a->n_rays, S_c, S_f, nc, nf);
+  if (t.total + slack > a->workspace_bytes) return fail("bwd: workspace too small");
+  const int64_t n = a->n_rays;
+  const int white = (a->flags & MOFA_FLAG_WHITE_BKGD) ? 1 : 0;
+  const float scale = a->loss_scale > 0.0f ? a->loss_scale : 1.0f;
+  const float inv = 1.0f / scale;
+  float* d_lat[4] = {nullptr, a->d_expmod, a->d_shape, a->d_tex};
+  CK(cudaMemsetAsync(a->d_rays, 0, sizeof(float) * 11 * n, s));
+  CK(cudaMemsetAsync(a->d_shape, 0, sizeof(float) * kNShape, s));
+  CK(cudaMemsetAsync(a->d_expmod, 0, sizeof(float) * kNExp, s));
+  CK(cudaMemsetAsync(a->d_tex, 0, sizeof(float) * kNTex, s));
+  // pass 1 = fine (rgb_map / acc_map), pass 0 = coarse (rgb0 / acc0, or the final maps when no fine pass ran)
+  for (int ps = fine ? 1 : 0; ps >= 0; --ps) {
+    const float* g_rgb = (ps == 1 || !fine) ? a->d_rgb : a->d_rgb0;
+    const float* g_acc = (ps == 1 || !fine) ? a->d_acc : a->d_acc0;
+    if (!g_rgb && !g_acc) continue;
+    Net& net = ps == 1 ? *nf : nc;
+    const int S = ps == 1 ? S_f : S_c;
+    const float* noise = ps == 1 ? a->noise_f : a->noise_c;
+    CK(launch_composite_bwd(t.pass[ps].raw, t.pass[ps].z, a->rays, a->ray_stride, noise, g_rgb, g_acc, scale, n, S, white,
+                            t.d_raw, a->d_rays, s));
+    c->launches++;
+    if (run_backward(c, net, t, t.pass[ps], n * S, inv, d_lat, s)) return 1;
+    CK(launch_pe_bwd(a->rays, a->ray_stride, t.pass[ps].z, t.dX0, t.dV, 128, n, S, a->d_rays, s));
+    c->launches++;
+  }
+  CK(launch_scale_f32(a->d_rays, inv, 11 * n, s));
+  c->launches++;
+  return 0;
+}
+
+int mofa_b200_raw2outputs_bwd(mofa_b200_ctx* c, const float* raw, const float* z, const float* rays, int stride,
+                              const float* noise, const float* d_rgb, const float* d_acc, int64_t n, int S,
+                              int white_bkgd, float* d_raw, float* d_rays, void* stream) {
+  if (!c) return fail("raw2outputs_bwd: ctx is NULL");
+  if (S < 2 || S > 256 || stride < 6) return fail("raw2outputs_bwd: bad sizes");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CK(cudaMemsetAsync(d_rays, 0, sizeof(float) * 11 * n, s));
+  CK(launch_composite_bwd(raw, z, rays, stride, noise, d_rgb, d_acc, 1.0f, n, S, white_bkgd, d_raw, d_rays, s));
   c->launches++;
   return 0;
 }

@@ -31,6 +31,12 @@ struct DenseLaunch {
   float* head_out;
   int head_n, head_stride, head_slot0;
   int store_c;          // 0: do not write C (only the head consumes this layer)
+  // backward-pass epilogue options: C = mask ⊙ (acc + r1_row ⊗ r1_col)
+  const __half* mask;
+  const float* r1_row;
+  const float* r1_col;
+  int r1_stride;
+  int64_t M_valid;      // rows that exist in mask / head_out (0 = M)
 };
 
 cudaError_t launch_dense_tc(const DenseLaunch& L, int num_sms, cudaStream_t stream);
@@ -76,5 +82,20 @@ cudaError_t launch_copy_f32(const float* src, float* dst, int64_t n, cudaStream_
 // raw[p] = (b_rgb[0..2] + sum of rgb partial slots, b_alpha + sum of alpha partial slots)
 cudaError_t launch_finalize_raw(const float* hp, int stride, int a_slot0, int a_tiles, int r_slot0, int r_tiles,
                                 const float* b_alpha, const float* b_rgb, float* raw, int64_t P, cudaStream_t s);
+
+// ---- backward pass (backward.cu) ----------------------------------------------------------------
+cudaError_t launch_composite_bwd(const float* raw, const float* z, const float* rays, int stride, const float* noise,
+                                 const float* d_rgb, const float* d_acc, float gscale, int64_t n, int S,
+                                 int white_bkgd, float* d_raw, float* d_rays, cudaStream_t s);
+cudaError_t launch_view_head_bwd(const float* d_raw, const float* w_rgb, const __half* HV, int Nh, int64_t P,
+                                 __half* dZ, cudaStream_t s);
+cudaError_t launch_colsum(const __half* dZ, int N, int64_t P, float* out, cudaStream_t s);
+cudaError_t launch_fold_bwd(const float* fold_w, int nlat, int N, const float* d_beff, float inv_scale, float* d_lat,
+                            cudaStream_t s);
+cudaError_t launch_pe_bwd(const float* rays, int stride, const float* z, const __half* dX0, const __half* dV, int ld,
+                          int64_t n, int S, float* d_rays, cudaStream_t s);
+cudaError_t launch_pack_weight_t(const float* src, int ld, int c0, int K, int krows_pad, int N, __half* dst,
+                                 cudaStream_t s);
+cudaError_t launch_scale_f32(float* x, float a, int64_t n, cudaStream_t s);
 
 }  // namespace mofa

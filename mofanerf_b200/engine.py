@@ -37,6 +37,7 @@ class Engine:
         self._net_keys = {0: None, 1: None}
         self._keep = {}   # fp32 staging tensors kept alive until the stream has consumed them
         self.chunk_rays = 0
+        self.max_train_bytes = 64 << 30
 
     def close(self):
         if getattr(self, "_h", None):
@@ -110,7 +111,7 @@ class Engine:
                     t_rand: Optional[torch.Tensor] = None, u: Optional[torch.Tensor] = None,
                     noise_c: Optional[torch.Tensor] = None, noise_f: Optional[torch.Tensor] = None,
                     want_aux: bool = False, gemm_simt: bool = False,
-                    chunk_rays: Optional[int] = None) -> Dict[str, torch.Tensor]:
+                    chunk_rays: Optional[int] = None, train: bool = False) -> Dict[str, torch.Tensor]:
         """rays [N, >=11] fp32 on this device -> dict with the reference's render_rays keys
         (models/render_class.py:338-345)."""
         if rays.device != self.device:
@@ -138,8 +139,18 @@ class Engine:
         chunk = self.chunk_rays if chunk_rays is None else int(chunk_rays)
         extra = [None if x is None else _f32c(x, dev) for x in (t_rand, u, noise_c, noise_f)]
         with torch.cuda.device(dev):
-            nbytes = self.lib.mofa_b200_workspace_bytes(self._h, n, N_samples, N_importance if fine else 0, chunk)
-            ws = self._workspace(nbytes)
+            if train:   # activations of every layer are kept: the workspace belongs to this call (returned)
+                nbytes = self.lib.mofa_b200_train_workspace_bytes(self._h, n, N_samples, N_importance if fine else 0,
+                                                                  int(fine_net))
+                if nbytes == 0:
+                    raise RuntimeError("mofa_b200: networks must be loaded before a training-mode render")
+                if nbytes > self.max_train_bytes:
+                    raise RuntimeError(f"training-mode render of {n} rays needs {nbytes / 2**30:.1f} GiB of activations "
+                                       f"(limit {self.max_train_bytes / 2**30:.0f} GiB): use a smaller ray batch")
+                ws = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
+            else:
+                nbytes = self.lib.mofa_b200_workspace_bytes(self._h, n, N_samples, N_importance if fine else 0, chunk)
+                ws = self._workspace(nbytes)
             a = _lib.RenderArgs()
             a.struct_size = C.sizeof(_lib.RenderArgs)
             a.flags = ((_lib.FLAG_LINDISP if lindisp else 0) | (_lib.FLAG_WHITE_BKGD if white_bkgd else 0) |
@@ -157,9 +168,41 @@ class Engine:
             a.weights = _ptr(out.get("weights"))
             a.z_vals = _ptr(out.get("z_vals"))
             a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
-            _lib.check(self.lib.mofa_b200_render_rays_fwd(self._h, C.byref(a), self._stream()))
+            fn = self.lib.mofa_b200_render_rays_train_fwd if train else self.lib.mofa_b200_render_rays_fwd
+            _lib.check(fn(self._h, C.byref(a), self._stream()))
         self._keep["extra"] = (rays, extra)
+        if train:
+            out["_train_ws"] = ws
+            out["_rays"] = rays
+            out["_noise"] = (extra[2], extra[3])
         return out
+
+    def render_rays_bwd(self, saved: Dict[str, torch.Tensor], N_samples: int, N_importance: int, *, run_fine: bool,
+                        fine_net: int, white_bkgd: bool, lindisp: bool, d_rgb=None, d_acc=None, d_rgb0=None,
+                        d_acc0=None, loss_scale: float = 1.0):
+        """Backward of a training-mode render_rays: returns (d_rays [n,11], d_shape [50], d_expmod [30], d_tex [256])."""
+        rays, ws = saved["_rays"], saved["_train_ws"]
+        noise_c, noise_f = saved["_noise"]
+        dev, n = self.device, rays.shape[0]
+        f32 = dict(dtype=torch.float32, device=dev)
+        g = [None if x is None else _f32c(x, dev) for x in (d_rgb, d_acc, d_rgb0, d_acc0)]
+        d_rays = torch.empty(n, 11, **f32)
+        d_shape, d_exp, d_tex = torch.empty(50, **f32), torch.empty(30, **f32), torch.empty(256, **f32)
+        with torch.cuda.device(dev):
+            a = _lib.BwdArgs()
+            a.struct_size = C.sizeof(_lib.BwdArgs)
+            a.flags = (_lib.FLAG_LINDISP if lindisp else 0) | (_lib.FLAG_WHITE_BKGD if white_bkgd else 0)
+            a.rays, a.n_rays, a.ray_stride = rays.data_ptr(), n, rays.stride(0)
+            a.n_samples, a.n_importance = int(N_samples), int(N_importance)
+            a.run_fine, a.fine_net = int(bool(run_fine)), int(fine_net)
+            a.noise_c, a.noise_f = _ptr(noise_c), _ptr(noise_f)
+            a.d_rgb, a.d_acc, a.d_rgb0, a.d_acc0 = [_ptr(x) for x in g]
+            a.loss_scale = float(loss_scale)
+            a.d_rays, a.d_shape, a.d_expmod, a.d_tex = d_rays.data_ptr(), d_shape.data_ptr(), d_exp.data_ptr(), d_tex.data_ptr()
+            a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+            _lib.check(self.lib.mofa_b200_render_rays_bwd(self._h, C.byref(a), self._stream()))
+        self._keep["bwd"] = g
+        return d_rays, d_shape, d_exp, d_tex
 
     def run_network(self, which: int, pts: torch.Tensor, viewdirs: torch.Tensor, gemm_simt: bool = False) -> torch.Tensor:
         """pts [..., 3], viewdirs broadcastable to pts -> raw [..., 4]  (models/render_class.py:69-94)."""
@@ -196,6 +239,21 @@ class Engine:
                                                       n, S, int(white_bkgd), rgb.data_ptr(), disp.data_ptr(),
                                                       acc.data_ptr(), w.data_ptr(), depth.data_ptr(), self._stream()))
         return rgb, disp, acc, w, depth
+
+    def composite_bwd(self, raw, z_vals, rays, noise, d_rgb, d_acc, white_bkgd=False):
+        """Adjoint of raw2outputs: returns (d_raw [n,S,4], d_rays [n,11] with the |rays_d| term in columns 3..5)."""
+        raw, z, ry = _f32c(raw, self.device), _f32c(z_vals, self.device), _f32c(rays, self.device)
+        nz = None if noise is None else _f32c(noise, self.device)
+        gr = None if d_rgb is None else _f32c(d_rgb, self.device)
+        ga = None if d_acc is None else _f32c(d_acc, self.device)
+        n, S = z.shape
+        d_raw = torch.empty(n, S, 4, dtype=torch.float32, device=self.device)
+        d_rays = torch.empty(n, 11, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.mofa_b200_raw2outputs_bwd(self._h, raw.data_ptr(), z.data_ptr(), ry.data_ptr(), ry.stride(0),
+                                                          _ptr(nz), _ptr(gr), _ptr(ga), n, S, int(white_bkgd),
+                                                          d_raw.data_ptr(), d_rays.data_ptr(), self._stream()))
+        return d_raw, d_rays
 
     def sample_pdf_merge(self, z_vals, weights, N_importance, u=None):
         z, w = _f32c(z_vals, self.device), _f32c(weights, self.device)

@@ -142,11 +142,8 @@ class B200Renderer(torch.nn.Module):
         rays = self.rays[ray_batch[0]:ray_batch[1]]
         if rays.shape[-1] < 11:
             raise NotImplementedError("use_viewdirs=False is not supported (the MoFaNeRF nets require view dirs)")
-        exp_in = self.expCodes_Sigma[self.expType] if self.expType == 20 else None   # caller-supplied code (fitting)
-        if _needs_grad(rays, self.shapeCodes, self.decoding_texCodes, exp_in):
-            raise NotImplementedError(
-                "B200Renderer: gradients through render_rays (fitting/training) are SURVEY.md §8 row f1 — "
-                "forward only in this version; call under torch.no_grad()")
+        needs_grad = _needs_grad(rays, self.shapeCodes, self.decoding_texCodes, self.expCodes_Sigma[self.expType],
+                                 *self.idSpecificMod.parameters())
         n = rays.shape[0]
         fine = N_importance > 0 and self.is_run_fineNet
         if pytest:  # models/render_class.py:308-311,465-468; tools/run_nerf_helpers.py:218-226
@@ -163,14 +160,36 @@ class B200Renderer(torch.nn.Module):
                 if fine and noise_f is None:
                     np.random.seed(0)
                     noise_f = torch.Tensor(np.random.rand(n, N_samples + N_importance) * raw_noise_std)
-        eng = self._prepare(network_fn, network_fine, rays.device)
         self._call += 1
-        return eng.render_rays(rays, N_samples, N_importance, run_fine=self.is_run_fineNet,
-                               fine_net=(1 if network_fine is not None else 0), perturb=float(perturb),
-                               raw_noise_std=float(raw_noise_std), lindisp=bool(lindisp),
-                               white_bkgd=bool(white_bkgd), retraw=bool(retraw),
-                               seed=self.seed * 1000003 + self._call, t_rand=t_rand, u=u, noise_c=noise_c,
-                               noise_f=noise_f, want_aux=want_aux, gemm_simt=gemm_simt)
+        cfg = dict(N_samples=int(N_samples), N_importance=int(N_importance), run_fine=bool(self.is_run_fineNet),
+                   fine_net=(1 if network_fine is not None else 0), perturb=float(perturb),
+                   raw_noise_std=float(raw_noise_std), lindisp=bool(lindisp), white_bkgd=bool(white_bkgd),
+                   retraw=bool(retraw), seed=self.seed * 1000003 + self._call, t_rand=t_rand, u=u, noise_c=noise_c,
+                   noise_f=noise_f, want_aux=want_aux)
+        if needs_grad:
+            # fitting (run_fit.py:305-313): gradients w.r.t. rays (pose) and the three codes; weights are constants
+            if gemm_simt:
+                raise NotImplementedError("the SIMT verification kernel has no training mode")
+            from .autograd import RenderRaysFn
+            eng = self.engine(rays.device)
+            eng.load_network(0, network_fn)
+            if network_fine is not None:
+                eng.load_network(1, network_fine)
+            if raw_noise_std > 0. and noise_c is None:   # explicit draws so that backward sees the same noise
+                cfg["noise_c"] = torch.randn(n, N_samples, device=rays.device) * raw_noise_std
+                if fine:
+                    cfg["noise_f"] = torch.randn(n, N_samples + N_importance, device=rays.device) * raw_noise_std
+            shape = self.shapeCodes[0, :].reshape(-1).to(rays.device)
+            exp_mod = self._exp_mod().reshape(-1).to(rays.device)
+            tex = self.decoding_texCodes.reshape(-1).to(rays.device)
+            outs = RenderRaysFn.apply(rays, shape, exp_mod, tex, eng, cfg)
+            keys = ["rgb_map", "acc_map", "disp_map"] + (["rgb0", "acc0", "disp0", "z_std"] if fine else [])
+            keys += [k for k in (("raw",) if retraw else ()) + (("weights", "z_vals") if want_aux else ())]
+            return dict(zip(keys, outs))
+        eng = self._prepare(network_fn, network_fine, rays.device)
+        cfg.pop("want_aux")
+        return eng.render_rays(rays, cfg.pop("N_samples"), cfg.pop("N_importance"), want_aux=want_aux,
+                               gemm_simt=gemm_simt, **cfg)
 
     # ------------------------------------------------------------------ render / render_fitting
     def _rays_from_args(self, H, W, K, rays, c2w, ndc, near, far, use_viewdirs, c2w_staticcam):

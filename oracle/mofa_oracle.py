@@ -297,12 +297,14 @@ def coarse_z_vals(near, far, N_samples, lindisp=False, perturb=0.0, t_rand=None)
     return z_vals
 
 
-@torch.no_grad()
 def render_rays(rays: torch.Tensor, net_coarse: NeRF, net_fine: Optional[NeRF], shape_codes, exp_mod,
                 tex_codes, N_samples=64, N_importance=64, perturb=0.0, lindisp=False,
                 white_bkgd=False, retraw=False, t_rand=None, u=None, noise_c=None, noise_f=None,
-                multires=10, multires_views=4, netchunk=65536, run_fine=True) -> Dict[str, torch.Tensor]:
-    """rays [N,11] -> dict with the reference's keys (:338-345)."""
+                multires=10, multires_views=4, netchunk=65536, run_fine=True,
+                z_fine_override=None) -> Dict[str, torch.Tensor]:
+    """rays [N,11] -> dict with the reference's keys (:338-345).  Differentiable (call under torch.no_grad()
+    for inference).  z_fine_override: use these fine-pass depths instead of resampling (gradient tests compare
+    two implementations at identical sample points; the reference detaches z_samples anyway, :326)."""
     rays_o, rays_d = rays[:, 0:3], rays[:, 3:6]
     viewdirs = rays[:, 8:11]
     near, far = rays[:, 6:7], rays[:, 7:8]
@@ -316,7 +318,10 @@ def render_rays(rays: torch.Tensor, net_coarse: NeRF, net_fine: Optional[NeRF], 
         rgb0, disp0, acc0 = rgb_map, disp_map, acc_map
         z_mid = 0.5 * (z_vals[..., 1:] + z_vals[..., :-1])                                 # :324
         z_samples = sample_pdf(z_mid, weights[..., 1:-1], N_importance, det=(perturb == 0.0), u=u)
+        z_samples = z_samples.detach()                                                     # :326
         z_vals, _ = torch.sort(torch.cat([z_vals, z_samples], -1), -1)                     # :328
+        if z_fine_override is not None:
+            z_vals = z_fine_override
         pts = rays_o[..., None, :] + rays_d[..., None, :] * z_vals[..., :, None]
         run_fn = net_coarse if net_fine is None else net_fine                              # :332
         raw = run_network(pts, viewdirs, run_fn, shape_codes, exp_mod, tex_codes,

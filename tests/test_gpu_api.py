@@ -93,15 +93,19 @@ def test_latent_sweep_refolds_per_call():
     rays_o, rays_d = inp["rays_o"][:24], inp["rays_d"][:24]
     rays = O.make_ray_batch(rays_o, rays_d, 8.0, 26.0)
     g = torch.Generator().manual_seed(21)
-    outs = []
-    for i in range(3):
+    cases, outs = [], []
+    for i in range(3):      # oracle first (CPU), then the engine (the same modules move to the GPU)
         shape = inp["shape"] + 0.02 * torch.randn(1, 50, generator=g) * (i > 0)
         tex = inp["tex"] + 0.1 * torch.randn(256, generator=g) * (i > 1)
         exp = torch.rand(1, 30, generator=g)
         with torch.no_grad():
             ref = O.render_rays(rays, c, f, shape, O.expression_mod(s, shape, exp), tex)
+        cases.append((shape, tex, exp, ref))
+    kw = _kw(c, f)
+    for shape, tex, exp, ref in cases:
+        with torch.no_grad():
             rgb, _, _, ex = r.render_fitting(1, 24, None, rays=(rays_o.to(DEV), rays_d.to(DEV)), shapeCodes=shape.to(DEV),
-                                             uvCodes=tex.to(DEV), expType=20, expCodes=exp.to(DEV), **_kw(c, f))
+                                             uvCodes=tex.to(DEV), expType=20, expCodes=exp.to(DEV), **kw)
         assert (ex["rgb0"].cpu() - ref["rgb0"]).abs().max().item() <= 4e-3
         assert (rgb.cpu() - ref["rgb_map"]).abs().max().item() <= 6e-2
         outs.append(rgb.cpu())
