@@ -261,8 +261,9 @@ def expression_mod(style: nn.Module, shape_codes: torch.Tensor, exp_code: torch.
 
 
 def run_network(pts, viewdirs, net: NeRF, shape_codes, exp_mod, tex_codes,
-                multires=10, multires_views=4, netchunk: Optional[int] = 65536):
-    """pts [N,S,3], viewdirs [N,3] -> raw [N,S,4]."""
+                multires=10, multires_views=4, netchunk: Optional[int] = 65536, forward_fn=None):
+    """pts [N,S,3], viewdirs [N,3] -> raw [N,S,4].  forward_fn(net, emb, shp, emb_dirs, tex) replaces net(...)
+    (used by the tests' reduced-precision emulation)."""
     flat = pts.reshape(-1, pts.shape[-1])
     P = flat.shape[0]
     emb = torch.cat([embed(flat, multires), exp_mod.reshape(1, -1).expand(P, -1)], -1)   # :77-83
@@ -271,7 +272,8 @@ def run_network(pts, viewdirs, net: NeRF, shape_codes, exp_mod, tex_codes,
     emb_dirs = embed(dirs, multires_views)                                               # :90
     tex = tex_codes.reshape(1, -1).expand(P, -1)                                         # :104
     step = P if netchunk is None else netchunk
-    out = torch.cat([net(emb[i:i + step], shp[i:i + step], emb_dirs[i:i + step], tex[i:i + step])
+    call = net if forward_fn is None else (lambda *a: forward_fn(net, *a))
+    out = torch.cat([call(emb[i:i + step], shp[i:i + step], emb_dirs[i:i + step], tex[i:i + step])
                      for i in range(0, P, step)], 0)                                     # :105
     return out.reshape(list(pts.shape[:-1]) + [out.shape[-1]])
 
@@ -301,7 +303,7 @@ def render_rays(rays: torch.Tensor, net_coarse: NeRF, net_fine: Optional[NeRF], 
                 tex_codes, N_samples=64, N_importance=64, perturb=0.0, lindisp=False,
                 white_bkgd=False, retraw=False, t_rand=None, u=None, noise_c=None, noise_f=None,
                 multires=10, multires_views=4, netchunk=65536, run_fine=True,
-                z_fine_override=None) -> Dict[str, torch.Tensor]:
+                z_fine_override=None, forward_fn=None) -> Dict[str, torch.Tensor]:
     """rays [N,11] -> dict with the reference's keys (:338-345).  Differentiable (call under torch.no_grad()
     for inference).  z_fine_override: use these fine-pass depths instead of resampling (gradient tests compare
     two implementations at identical sample points; the reference detaches z_samples anyway, :326)."""
@@ -311,7 +313,7 @@ def render_rays(rays: torch.Tensor, net_coarse: NeRF, net_fine: Optional[NeRF], 
     z_vals = coarse_z_vals(near, far, N_samples, lindisp, perturb, t_rand)
     pts = rays_o[..., None, :] + rays_d[..., None, :] * z_vals[..., :, None]              # :315
     raw = run_network(pts, viewdirs, net_coarse, shape_codes, exp_mod, tex_codes,
-                      multires, multires_views, netchunk)
+                      multires, multires_views, netchunk, forward_fn)
     rgb_map, disp_map, acc_map, weights, depth_map = raw2outputs(raw, z_vals, rays_d, noise_c, white_bkgd)
     ret = {}
     if N_importance > 0 and run_fine:
@@ -325,7 +327,7 @@ def render_rays(rays: torch.Tensor, net_coarse: NeRF, net_fine: Optional[NeRF], 
         pts = rays_o[..., None, :] + rays_d[..., None, :] * z_vals[..., :, None]
         run_fn = net_coarse if net_fine is None else net_fine                              # :332
         raw = run_network(pts, viewdirs, run_fn, shape_codes, exp_mod, tex_codes,
-                          multires, multires_views, netchunk)
+                          multires, multires_views, netchunk, forward_fn)
         rgb_map, disp_map, acc_map, weights, depth_map = raw2outputs(raw, z_vals, rays_d, noise_f, white_bkgd)
         ret.update(rgb0=rgb0, disp0=disp0, acc0=acc0,
                    z_std=torch.std(z_samples, dim=-1, unbiased=False))                     # :345

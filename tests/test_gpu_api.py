@@ -106,8 +106,9 @@ def test_latent_sweep_refolds_per_call():
         with torch.no_grad():
             rgb, _, _, ex = r.render_fitting(1, 24, None, rays=(rays_o.to(DEV), rays_d.to(DEV)), shapeCodes=shape.to(DEV),
                                              uvCodes=tex.to(DEV), expType=20, expCodes=exp.to(DEV), **kw)
-        assert (ex["rgb0"].cpu() - ref["rgb0"]).abs().max().item() <= 4e-3
-        assert (rgb.cpu() - ref["rgb_map"]).abs().max().item() <= 6e-2
+        assert (ex["rgb0"].cpu() - ref["rgb0"]).abs().max().item() <= 4e-3      # coarse maps: no resampling feedback
+        d = (rgb.cpu() - ref["rgb_map"]).abs()
+        assert d.mean().item() <= 5e-3 and d.median().item() <= 2e-3, f"mean {d.mean().item():.2e} max {d.max().item():.2e}"
         outs.append(rgb.cpu())
     assert (outs[0] - outs[1]).abs().max().item() > 1e-3 and (outs[1] - outs[2]).abs().max().item() > 1e-3
 

@@ -1,10 +1,21 @@
 """Backward pass for fitting (run_fit.py:305-313) against torch.autograd through the oracle.
 
 Both sides are evaluated at IDENTICAL sample depths (the engine's fine depths are fed to the oracle through
-z_fine_override; the reference detaches the resampled depths, models/render_class.py:326), so the comparison
-isolates the gradient arithmetic: fp16 operands / fp32 accumulation in the dense layers with a power-of-two
-loss scale, fp32 everywhere else.  Stated tolerance: relative L2 error <= 3e-2 and cosine >= 0.999 per gradient
-tensor (measured ~1e-3 .. 1e-2); compositing backward alone (fp32): 1e-4 relative.
+z_fine_override; the reference detaches the resampled depths, models/render_class.py:326).  Two references:
+
+A ReLU network's gradient is DISCONTINUOUS in its activations: flipping the mask of a fraction f of the units per
+layer moves the gradient by ~sqrt(2 f L) (L = 27 layers), so forward differences of 1e-4 relative (f ~ 5e-5) already
+cost ~5 %.  The tests therefore split the claim:
+
+  (0) test_gradients_exact_when_no_relu_clips: biases shifted so that no pre-activation is negative (asserted on the
+      oracle) -> the network is affine in its hidden units, masks cannot flip, and every adjoint (dense transposes,
+      two-segment skip layers, rank-1 sigma head, rgb head, latent fold adjoints, positional-encoding adjoint,
+      compositing adjoint, loss scaling) is checked tightly: rel. L2 error <= 1e-2, cosine >= 0.9999.
+  (1) random-init nets vs the oracle with the engine's rounding emulated (tests/fp16_emulation.py; masks agree except
+      for ~1e-4-level accumulation-order differences): rel <= 0.1, cosine >= 0.995 (measured 1.5e-2 .. 8e-2).
+  (2) the same vs the plain fp32 oracle (fp16-chain forward differences ~5e-4): rel <= 0.6, cosine >= 0.88 — a sign or
+      missing-term bug gives cosine far below that.
+Compositing backward alone (pure fp32): 1e-4 relative.
 """
 import pytest
 import torch
@@ -45,11 +56,53 @@ def test_composite_backward_matches_autograd():
     assert e < 1e-4, f"d_rays_d rel {e:.2e}"
 
 
+def _make_relu_free(nets):
+    """Make every hidden pre-activation positive (so no ReLU ever clips and masks cannot differ between
+    implementations) without killing the signal: hidden weights become positive (0.05|W| + 0.02 W >= 0.03|W|) with
+    unit-order gain per layer, biases 0.5; inputs that can be negative (encodings, latents) enter with small weights.
+    The two output heads keep their mixed-sign weights."""
+    for net in nets[:2]:
+        gain = 256.0 / net.W       # positive matrices have gain ~ fan_in * mean|w|: keep it ~1 for any width
+        for name, m in net.named_modules():
+            if isinstance(m, torch.nn.Linear) and not name.startswith(("alpha_linear", "rgb_linear")):
+                m.weight.data = (0.05 * m.weight.data.abs() + 0.02 * m.weight.data) * gain
+                m.bias.data.fill_(0.5)
+        w0 = net.xyzEncode.linears1.Linear0.weight.data
+        w0.mul_(4.0 / gain)
+        w0[:, :3].mul_(0.03)                                             # raw xyz reaches |26|
+        net.xyzEncode.linears1.Linear0.bias.data.fill_(2.0)              # encodings are signed
+        net.linear_view_xyBMuv[0].bias.data.fill_(1.0)
+        net.alpha_linear[0].weight.data = net.alpha_linear[0].weight.data.abs() * (0.004 * gain)   # sigma > 0, semi-transparent
+        net.alpha_linear[0].bias.data.fill_(0.15)
+        net.rgb_linear.weight.data.mul_(0.1)                             # keep the sigmoid away from saturation
+
+
+def test_gradients_exact_when_no_relu_clips():
+    meta, inp, _ = load_case("small_w256")
+    nets = build_case_nets(meta)
+    _make_relu_free(nets)
+    res = _gradient_case("small_w256[affine]", meta, inp, nets, use0=True, check_positive=True)
+    for k, (e, cs) in res["fp16-emulated"][0].items():
+        assert e <= 1e-2 and cs >= 0.9999, f"affine-net grad {k}: rel {e:.3e} cos {cs:.6f}"
+
+
 @pytest.mark.parametrize("name,use0", [("small_w256", True), ("full_w1024", False), ("perturb_pytest", True)])
 def test_fitting_gradients_match_oracle_autograd(name, use0):
-    from mofanerf_b200 import B200Renderer
     meta, inp, _ = load_case(name)
-    c, f, s = build_case_nets(meta)
+    results = _gradient_case(name, meta, inp, build_case_nets(meta), use0)
+    for k, (e, cs) in results["fp16-emulated"][0].items():
+        assert e <= 0.1 and cs >= 0.995, f"{name} grad {k} vs fp16-emulated oracle: rel {e:.3e} cos {cs:.5f}"
+    for k, (e, cs) in results["fp32"][0].items():
+        assert e <= 0.6 and cs >= 0.88, f"{name} grad {k} vs fp32 oracle: rel {e:.3e} cos {cs:.5f}"
+
+
+def _gradient_case(name, meta, inp, nets, use0, check_positive=False):
+    from mofanerf_b200 import B200Renderer
+    c, f, s = nets
+    if check_positive:
+        mins = []
+        hooks = [m.register_forward_hook(lambda mod, i, o: mins.append(float(i[0].min())))
+                 for net in (c, f) for m in net.modules() if isinstance(m, torch.nn.ReLU)]
     n = min(32, inp["rays_o"].shape[0])
     ro, rd = inp["rays_o"][:n].clone(), inp["rays_d"][:n].clone()
     rnd = {k: (None if v is None else v[:n]) for k, v in case_randoms(meta, inp["rays_o"].shape[0]).items()}
@@ -82,19 +135,27 @@ def test_fitting_gradients_match_oracle_autograd(name, use0):
     z_fine = ex["z_vals"].detach().cpu()
     c.cpu(); f.cpu()
 
-    # ---------------- oracle (CPU fp32), autograd, same fine depths
-    ol = dict(ro=ro.clone().requires_grad_(True), rd=rd.clone().requires_grad_(True),
-              shape=inp["shape"].clone().requires_grad_(True), tex=inp["tex"].clone().requires_grad_(True),
-              exp=inp["exp"].clone().requires_grad_(True))
-    rays = O.make_ray_batch(ol["ro"], ol["rd"], float(meta["near"]), float(meta["far"]))
-    em = O.expression_mod(s, ol["shape"], ol["exp"])
-    out = O.render_rays(rays, c, f, ol["shape"], em, ol["tex"], N_samples=int(meta["N_samples"]),
-                        N_importance=int(meta["N_importance"]), perturb=float(meta["perturb"]),
-                        white_bkgd=bool(meta["white_bkgd"]), lindisp=bool(meta["lindisp"]), z_fine_override=z_fine, **rnd)
-    loss_of(out).backward()
-    msgs = []
-    for k in ("shape", "tex", "exp", "ro", "rd"):
-        e, cs = _rel(got[k], ol[k].grad)
-        msgs.append(f"{k}: rel {e:.2e} cos {cs:.5f}")
-        assert e <= 3e-2 and cs >= 0.999, f"{name} grad {k}: rel {e:.3e} cos {cs:.5f} |ref| {ol[k].grad.norm().item():.3e}"
-    print(f"[parity] {name} gradients: " + "; ".join(msgs))
+    # ---------------- oracle (CPU), autograd, same fine depths: fp16-emulating and plain fp32
+    from tests.fp16_emulation import nerf_forward_fp16
+    results = {}
+    for label, fwd in (("fp16-emulated", nerf_forward_fp16), ("fp32", None)):
+        ol = dict(ro=ro.clone().requires_grad_(True), rd=rd.clone().requires_grad_(True),
+                  shape=inp["shape"].clone().requires_grad_(True), tex=inp["tex"].clone().requires_grad_(True),
+                  exp=inp["exp"].clone().requires_grad_(True))
+        rays = O.make_ray_batch(ol["ro"], ol["rd"], float(meta["near"]), float(meta["far"]))
+        em = O.expression_mod(s, ol["shape"], ol["exp"])
+        out = O.render_rays(rays, c, f, ol["shape"], em, ol["tex"], N_samples=int(meta["N_samples"]),
+                            N_importance=int(meta["N_importance"]), perturb=float(meta["perturb"]),
+                            white_bkgd=bool(meta["white_bkgd"]), lindisp=bool(meta["lindisp"]), z_fine_override=z_fine,
+                            forward_fn=fwd, **rnd)
+        loss_of(out).backward()
+        fwd_err = (out["rgb_map"].detach() - rgb.detach().cpu()).abs().max().item()
+        results[label] = ({k: _rel(got[k], ol[k].grad) for k in ("shape", "tex", "exp", "ro", "rd")}, fwd_err)
+    for label, (res, fwd_err) in results.items():
+        print(f"[parity] {name} gradients vs {label} oracle (forward max|d rgb| {fwd_err:.1e}): " +
+              "; ".join(f"{k}: rel {e:.2e} cos {cs:.5f}" for k, (e, cs) in res.items()))
+    if check_positive:
+        for h in hooks:
+            h.remove()
+        assert min(mins) > 0.0, f"a pre-activation went negative ({min(mins):.3f}): the net is not affine"
+    return results

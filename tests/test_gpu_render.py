@@ -194,14 +194,20 @@ def test_run_network_matches_nerf_forward():
     assert d.max().item() <= 2e-2 * max(1.0, scale)
 
 
-def test_grad_request_is_refused_loudly():
+def test_training_mode_forward_equals_inference_forward():
+    """With grad-requiring inputs the renderer switches to the activation-keeping forward (fitting); its outputs
+    must equal the inference path bit for bit."""
     from mofanerf_b200 import B200Renderer
     meta, inp, _ = load_case("small_w256")
     c, f, s = build_case_nets(meta)
     r = B200Renderer(expCodesLen=30).to(DEV)
-    shape = inp["shape"].to(DEV).requires_grad_(True)
-    with pytest.raises(NotImplementedError):
-        r.render_fitting(4, 4, None, rays=(inp["rays_o"][:16].to(DEV), inp["rays_d"][:16].to(DEV)), shapeCodes=shape,
-                         uvCodes=inp["tex"].to(DEV), expType=20, expCodes=inp["exp"].to(DEV), near=8., far=26.,
-                         use_viewdirs=True, ndc=False, network_fn=c.to(DEV), network_fine=f.to(DEV), N_samples=64,
-                         N_importance=64)
+    r.idSpecificMod.load_state_dict(s.state_dict())
+    args = dict(rays=(inp["rays_o"][:16].to(DEV), inp["rays_d"][:16].to(DEV)), uvCodes=inp["tex"].to(DEV), expType=20,
+                expCodes=inp["exp"].to(DEV), near=8., far=26., use_viewdirs=True, ndc=False, network_fn=c.to(DEV),
+                network_fine=f.to(DEV), N_samples=64, N_importance=64)
+    with torch.no_grad():
+        a = r.render_fitting(4, 4, None, shapeCodes=inp["shape"].to(DEV), **args)
+    b = r.render_fitting(4, 4, None, shapeCodes=inp["shape"].to(DEV).requires_grad_(True), **args)
+    assert b[0].requires_grad and b[0].grad_fn is not None
+    assert torch.equal(a[0], b[0].detach()) and torch.equal(a[2], b[2].detach())
+    assert torch.equal(a[3]["rgb0"], b[3]["rgb0"].detach())
