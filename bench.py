@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--chunk-rays", type=int, default=0, help="engine-internal rays per pass (0 = default)")
     ap.add_argument("--cpu-sample-rays", type=int, default=0, help="rays in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="frame", choices=["frame", "fit"],
+                    help="frame: BASELINE metric (800x800 FULL render); fit: run_fit.py iteration (1024 rays, fwd+bwd+Adam)")
     return ap.parse_args()
 
 
@@ -221,8 +223,68 @@ def workload_config(args):
             "l2": "working set (activation buffers, >1 GB per pass) >> 126 MB L2; 256 MB scratch write between timed steps"}
 
 
+def run_fit_workload(args):
+    """BASELINE config #3: one run_fit.py fitting iteration = 1024 random rays, FULL pipeline, forward + backward to the
+    latent codes and the pose, L1 loss, three Adam steps (run_fit.py:281-313).  Not the headline metric: printed as its own
+    JSON line for the record."""
+    dev = torch.device("cuda", 0)
+    import __graft_entry__
+    __graft_entry__.build()
+    from mofanerf_b200 import B200Renderer, nets
+    coarse, fine, style = nets.build_nets(0, device=dev)
+    shape, tex, exp, ro, rd = synth_inputs(256, 256)
+    r = B200Renderer(expCodesLen=30).to(dev)
+    r.idSpecificMod.load_state_dict(style.state_dict())
+    n = 1024
+    g = torch.Generator().manual_seed(0)
+    kw = dict(near=8.0, far=26.0, use_viewdirs=True, ndc=False, network_fn=coarse, network_fine=fine,
+              N_samples=args.n_samples, N_importance=args.n_importance, perturb=0.0, raw_noise_std=0.0)
+    shape = shape.to(dev).requires_grad_(True)
+    tex = tex.to(dev).requires_grad_(True)
+    exp = exp.to(dev).requires_grad_(True)
+    pose_delta = torch.zeros(3, device=dev, requires_grad=True)
+    light = torch.ones(1, device=dev, requires_grad=True)
+    opts = [torch.optim.Adam([light, pose_delta], lr=2e-3), torch.optim.Adam([tex], lr=2e-3),
+            torch.optim.Adam([exp, shape], lr=4e-3)]
+    target = torch.rand(n, 3, device=dev)
+    ro_d, rd_d = ro.to(dev), rd.to(dev)
+    l1 = torch.nn.L1Loss()
+
+    def step():
+        idx = torch.randint(0, ro_d.shape[0], (n,), generator=g).to(dev)
+        rgb = r.render_fitting(1, n, None, rays=(ro_d[idx] + pose_delta, rd_d[idx]), shapeCodes=shape, uvCodes=tex,
+                               expType=20, expCodes=exp, **kw)[0]
+        loss = l1(rgb * light, target)
+        for o in opts:
+            o.zero_grad()
+        loss.backward()
+        for o in opts:
+            o.step()
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    iters = max(10, args.steps)
+    e0.record()
+    for _ in range(iters):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    fwd = n * (args.n_samples * FLOP_COARSE_PT + (args.n_samples + args.n_importance) * FLOP_FINE_PT)
+    bwd = n * (args.n_samples + args.n_importance) * FLOP_FINE_PT       # dX only, fine pass only (rgb0 is not in the loss)
+    print(json.dumps({"metric": "fit iterations/s (run_fit.py: 1024 rays, 64+128 samples, fwd+bwd+Adam)", "value": 1e3 / ms,
+                      "unit": "it/s", "ms_per_iter": ms, "rays_per_s": n * 1e3 / ms, "n_gpus": 1,
+                      "algorithmic_tflops": (fwd + bwd) / (ms / 1e3) / 1e12, "data": "synthetic",
+                      "config": {"workload": "BASELINE config #3: fitting loop, N_rand=1024, FULL, 1 x B200"}}), flush=True)
+
+
 def main():
     args = parse()
+    if args.workload == "fit" and args.impl == "b200":
+        run_fit_workload(args)
+        return
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

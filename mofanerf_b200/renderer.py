@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import os
 import time
+import warnings
 from typing import Optional
 
 import numpy as np
@@ -54,6 +55,8 @@ def _needs_grad(*tensors) -> bool:
 
 
 class B200Renderer(torch.nn.Module):
+    _warned_weights = False
+
     def __init__(self, embed_fn=None, embeddirs_fn=None, netchunk=1024 * 64, uvCodesLen=256, expCodesLen=4,
                  input_ch=3, shapeCodes=50):
         super().__init__()
@@ -168,6 +171,10 @@ class B200Renderer(torch.nn.Module):
                    noise_f=noise_f, want_aux=want_aux)
         if needs_grad:
             # fitting (run_fit.py:305-313): gradients w.r.t. rays (pose) and the three codes; weights are constants
+            if not B200Renderer._warned_weights:
+                B200Renderer._warned_weights = True
+                warnings.warn("mofanerf_b200: autograd through render_rays propagates to rays (pose) and the shape / texture / "
+                              "expression codes; gradients w.r.t. the NeRF weights are not computed (SURVEY.md §8 row f2)")
             if gemm_simt:
                 raise NotImplementedError("the SIMT verification kernel has no training mode")
             from .autograd import RenderRaysFn

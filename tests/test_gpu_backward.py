@@ -159,3 +159,42 @@ def _gradient_case(name, meta, inp, nets, use0, check_positive=False):
             h.remove()
         assert min(mins) > 0.0, f"a pre-activation went negative ({min(mins):.3f}): the net is not affine"
     return results
+
+
+def test_fitting_loop_recovers_latents_direction():
+    """BASELINE config #3 in miniature (run_fit.py:257-313): L1 loss against a target rendered with other codes,
+    three Adam optimisers over pose-free latents; the loss must fall substantially in 40 iterations."""
+    from mofanerf_b200 import B200Renderer
+    meta, inp, _ = load_case("small_w256")
+    c, f, s = build_case_nets(meta)
+    r = B200Renderer(expCodesLen=30).to(DEV)
+    r.idSpecificMod.load_state_dict(s.state_dict())
+    n = 128
+    ro, rd = inp["rays_o"][:n].to(DEV), inp["rays_d"][:n].to(DEV)
+    kw = dict(near=8.0, far=26.0, use_viewdirs=True, ndc=False, network_fn=c.to(DEV), network_fine=f.to(DEV),
+              N_samples=64, N_importance=64, perturb=0.0, raw_noise_std=0.0)
+    g = torch.Generator().manual_seed(3)
+    tgt_shape = (inp["shape"] + 0.05 * torch.randn(1, 50, generator=g)).to(DEV)
+    tgt_tex = (inp["tex"] + 0.3 * torch.randn(256, generator=g)).to(DEV)
+    tgt_exp = torch.rand(1, 30, generator=g).to(DEV)
+    with torch.no_grad():
+        target = r.render_fitting(1, n, None, rays=(ro, rd), shapeCodes=tgt_shape, uvCodes=tgt_tex, expType=20,
+                                  expCodes=tgt_exp, **kw)[0]
+    shape = inp["shape"].to(DEV).clone().requires_grad_(True)
+    tex = inp["tex"].to(DEV).clone().requires_grad_(True)
+    exp = inp["exp"].to(DEV).clone().requires_grad_(True)
+    light = torch.ones(1, device=DEV, requires_grad=True)
+    opts = [torch.optim.Adam([light], lr=2e-3), torch.optim.Adam([tex], lr=2e-2), torch.optim.Adam([exp, shape], lr=4e-3)]
+    l1 = torch.nn.L1Loss()
+    losses = []
+    for it in range(40):
+        rgb = r.render_fitting(1, n, None, rays=(ro, rd), shapeCodes=shape, uvCodes=tex, expType=20, expCodes=exp, **kw)[0]
+        loss = l1(rgb * light, target)
+        for o in opts:
+            o.zero_grad()
+        loss.backward()
+        for o in opts:
+            o.step()
+        losses.append(float(loss))
+    print(f"[fit] L1 loss {losses[0]:.4f} -> {losses[-1]:.4f} over 40 iterations")
+    assert losses[-1] < 0.6 * losses[0], losses
