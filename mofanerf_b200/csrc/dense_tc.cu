@@ -92,8 +92,8 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   const int num_tiles = p.m_tiles * p.n_tiles;
   const int total_kb = p.kb0 + p.kb1;
 
-  if (warp == 0 && lane == 0) {
-    // ------------------------------------------------------------------ TMA producer
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (whole warp, one elected lane issues)
     int stage = 0;
     uint32_t phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
@@ -102,25 +102,28 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       for (int kb = 0; kb < total_kb; ++kb) {
         mbar_wait(empty0 + 8 * stage, phase ^ 1u);
         const uint32_t fb = full0 + 8 * stage;
-        mbar_expect_tx(fb, L::STAGE_BYTES);
         const uint32_t sa = base + stage * L::STAGE_BYTES;
         const uint32_t sb = sa + L::A_BYTES;
-        if (kb < p.kb0) {
-          tma_load_2d(sa, &tmA0, fb, kb * 64, m0);
-          tma_load_2d(sb, &tmB0, fb, kb * 64, n0);
-        } else {
-          const int k = (kb - p.kb0) * 64;
-          tma_load_2d(sa, &tmA1, fb, k, m0);
-          tma_load_2d(sb, &tmB1, fb, k, n0);
+        if (elect_one()) {
+          mbar_expect_tx(fb, L::STAGE_BYTES);
+          if (kb < p.kb0) {
+            tma_load_2d(sa, &tmA0, fb, kb * 64, m0);
+            tma_load_2d(sb, &tmB0, fb, kb * 64, n0);
+          } else {
+            const int k = (kb - p.kb0) * 64;
+            tma_load_2d(sa, &tmA1, fb, k, m0);
+            tma_load_2d(sb, &tmB1, fb, k, n0);
+          }
         }
+        __syncwarp();
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1u;
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ------------------------------------------------------------------ MMA issuer
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (whole warp, one elected lane issues)
     constexpr uint32_t idesc = umma_idesc_f16_f32(128, BN);
     int stage = 0;
     uint32_t phase = 0;
@@ -137,17 +140,20 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         const uint32_t sa = base + stage * L::STAGE_BYTES;
         const uint64_t da = umma_desc_sw128_kmajor(sa);
         const uint64_t db = umma_desc_sw128_kmajor(sa + L::A_BYTES);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {               // 4 x (K=16): +32 B along the swizzled row
-          umma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) {             // 4 x (K=16): +32 B along the swizzled row
+            umma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty0 + 8 * stage);          // frees the smem slot when these MMAs retire
+          if (kb == total_kb - 1) umma_commit(tfull0 + 8 * as);   // accumulator ready for the epilogue
         }
-        umma_commit(empty0 + 8 * stage);            // frees the smem slot when these MMAs retire
+        __syncwarp();
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1u;
         }
       }
-      umma_commit(tfull0 + 8 * as);                 // accumulator ready for the epilogue
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue

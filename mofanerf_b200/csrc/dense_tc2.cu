@@ -14,6 +14,8 @@
 //   warp 2        : TMEM allocator (cta_group::2, both CTAs)
 //   warps 4..7    : epilogue of this CTA's 128 rows (TMEM -> +bias, ReLU -> fp16 -> swizzled smem -> TMA store);
 //                   one lane per warp releases the accumulator stage on the leader's barrier (remote arrive)
+#include <cstdlib>
+
 #include "dense_epilogue.cuh"
 #include "engine.h"
 #include "ptx.cuh"
@@ -36,7 +38,10 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
   return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  // default (release, CTA-scope) semantics as CUTLASS's ClusterBarrier::arrive(cta_id): the accumulator hand-off is
+  // ordered by tcgen05.wait::ld + tcgen05.fence::before_thread_sync, not by generic-memory release at cluster scope
+  // (the explicit .release.cluster form compiled to MEMBAR.ALL.CTA + ERRBAR = 40 % of the epilogue warps' samples)
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void tma_load_2d_cg2(uint32_t smem_dst, const void* tmap, uint32_t bar_cluster_addr,
                                                 int c0, int c1) {
@@ -45,6 +50,11 @@ __device__ __forceinline__ void tma_load_2d_cg2(uint32_t smem_dst, const void* t
       " [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
       : "memory");
+}
+// L2 prefetch of a tile that a later TMA load will fetch (no smem, no barrier)
+__device__ __forceinline__ void tma_prefetch_l2_2d(const void* tmap, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void tmem_alloc_cg2(uint32_t smem_result_addr, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
@@ -78,6 +88,7 @@ struct Dense2Params {
   int m_tiles;   // 256-row pair tiles
   int n_tiles;   // 256-column tiles
   int kb0, kb1;
+  int prefetch;   // L2-prefetch the next m-block's activation rows
 };
 
 template <int STAGES>
@@ -150,36 +161,50 @@ dense_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   const int pair = blockIdx.x >> 1;
   const int num_pairs = gridDim.x >> 1;
 
-  if (warp == 0 && lane == 0) {
-    // ------------------------------------------------------------------ TMA producer (both CTAs)
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs; whole warp, one elected lane issues)
     int stage = 0;
     uint32_t phase = 0;
     for (int t = pair; t < num_tiles; t += num_pairs) {
       const int m0 = (t / p.n_tiles) * 256 + static_cast<int>(rank) * 128;
       const int n0 = (t % p.n_tiles) * BN + static_cast<int>(rank) * 128;
+      // Activation rows come from HBM on first touch.  The four n-tiles of an m-block run on four neighbouring pairs
+      // at about the same time; the pair whose NEXT tile is the n = 0 tile of an m-block starts that m-block's rows
+      // towards L2 one whole tile (~6 us) ahead, so that the 6-stage smem ring only has to cover L2 latency.
+      {
+        const int tn = t + num_pairs;
+        if (p.prefetch && tn < num_tiles && (tn % p.n_tiles) == 0 && elect_one()) {
+          const int pm0 = (tn / p.n_tiles) * 256 + static_cast<int>(rank) * 128;
+          for (int kb = 0; kb < p.kb0; ++kb) tma_prefetch_l2_2d(&tmA0, kb * 64, pm0);
+          for (int kb = 0; kb < p.kb1; ++kb) tma_prefetch_l2_2d(&tmA1, kb * 64, pm0);
+        }
+      }
       for (int kb = 0; kb < total_kb; ++kb) {
         mbar_wait(empty0 + 8 * stage, phase ^ 1u);
         const uint32_t fb_local = full0 + 8 * stage;
-        if (leader) mbar_expect_tx(fb_local, 2 * L::STAGE_BYTES);      // bytes of both CTAs land on this barrier
         const uint32_t fb = mapa_u32(fb_local, 0);
         const uint32_t sa = base + stage * L::STAGE_BYTES;
         const uint32_t sb = sa + L::A_BYTES;
-        if (kb < p.kb0) {
-          tma_load_2d_cg2(sa, &tmA0, fb, kb * 64, m0);
-          tma_load_2d_cg2(sb, &tmB0, fb, kb * 64, n0);
-        } else {
-          const int k = (kb - p.kb0) * 64;
-          tma_load_2d_cg2(sa, &tmA1, fb, k, m0);
-          tma_load_2d_cg2(sb, &tmB1, fb, k, n0);
+        if (elect_one()) {
+          if (leader) mbar_expect_tx(fb_local, 2 * L::STAGE_BYTES);    // bytes of both CTAs land on this barrier
+          if (kb < p.kb0) {
+            tma_load_2d_cg2(sa, &tmA0, fb, kb * 64, m0);
+            tma_load_2d_cg2(sb, &tmB0, fb, kb * 64, n0);
+          } else {
+            const int k = (kb - p.kb0) * 64;
+            tma_load_2d_cg2(sa, &tmA1, fb, k, m0);
+            tma_load_2d_cg2(sb, &tmB1, fb, k, n0);
+          }
         }
+        __syncwarp();
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1u;
         }
       }
     }
-  } else if (warp == 1 && lane == 0 && leader) {
-    // ------------------------------------------------------------------ MMA issuer (leader CTA)
+  } else if (warp == 1 && leader) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA; whole warp, one elected lane issues)
     constexpr uint32_t idesc = umma_idesc_f16_f32(256, BN);
     int stage = 0;
     uint32_t phase = 0;
@@ -196,17 +221,20 @@ dense_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         const uint32_t sa = base + stage * L::STAGE_BYTES;
         const uint64_t da = umma_desc_sw128_kmajor(sa);
         const uint64_t db = umma_desc_sw128_kmajor(sa + L::A_BYTES);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          umma_f16_ss_cg2(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) {
+            umma_f16_ss_cg2(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit_cg2_mc(empty0 + 8 * stage, 0x3);   // frees this stage in BOTH CTAs
+          if (kb == total_kb - 1) umma_commit_cg2_mc(tfull0 + 8 * as, 0x3);   // accumulator halves ready in both CTAs
         }
-        umma_commit_cg2_mc(empty0 + 8 * stage, 0x3);   // frees this stage in BOTH CTAs
+        __syncwarp();
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1u;
         }
       }
-      umma_commit_cg2_mc(tfull0 + 8 * as, 0x3);        // accumulator halves ready in both CTAs
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue (both CTAs, own 128 rows)
@@ -255,6 +283,11 @@ cudaError_t launch_dense_tc2(const DenseLaunch& L, int num_sms, cudaStream_t str
   p.n_tiles = L.N / 256;
   p.kb0 = L.K[0] / 64;
   p.kb1 = L.K[1] / 64;
+  {
+    // measured: -4 % on the fine-net layers (the extra L2 requests cost more than the latency they hide) => opt-in only
+    static const int pf = [] { const char* v = getenv("MOFA_B200_L2_PREFETCH"); return (v && v[0] == '1') ? 1 : 0; }();
+    p.prefetch = pf;
+  }
   const long long tiles = static_cast<long long>(p.m_tiles) * p.n_tiles;
   if (tiles <= 0) return cudaSuccess;
   const int max_pairs = num_sms / 2;

@@ -10,6 +10,20 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// One elected lane of a fully converged warp.  Used instead of `lane == 0` around TMA / tcgen05 issue: those SASS
+// instructions take UNIFORM registers, and only inside an elect.sync region does the compiler keep the (warp-uniform)
+// descriptors in uniform registers; under a `lane == 0` branch it emitted an ELECT + 5x R2UR.BROADCAST + BRA.U.ANY loop
+// around every UTCHMMA, which made the issuing thread the bottleneck (ncu: 85 % of its samples in that sequence).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");

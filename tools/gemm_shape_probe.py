@@ -17,7 +17,7 @@ M, N, K = 262144, 1024, 1024
 g = torch.Generator().manual_seed(0)
 A = (torch.randn(M, K, generator=g) * 0.5).half().to(dev)
 B = (torch.randn(M, K, generator=g) * 0.5).half().to(dev)
-W = (torch.randn(N, K, generator=g) * 0.03).half().to(dev)
+W = (torch.randn(N, K, generator=g) * (2.0 / K) ** 0.5).half().to(dev)   # He init: ReLU activations keep their scale
 bias = torch.zeros(N, device=dev)
 eng = get_engine(dev)
 flops = 2.0 * M * N * K
@@ -46,6 +46,7 @@ state = {"a": A, "b": B}
 
 def cublas():
     torch.matmul(state["a"], W.t(), out=state["b"])
+    torch.relu_(state["b"])          # keep the data alive (all-zero operands draw less power and clock higher)
     state["a"], state["b"] = state["b"], state["a"]
 
 
@@ -56,7 +57,15 @@ def make(mode):
     return f
 
 
-res = {"shape": [M, N, K], "cublas_fp16_tflops": loop(cublas)}
+res = {"shape": [M, N, K], "note": "cuBLAS figure includes a separate relu_ kernel per GEMM (~0.17 ms of ~0.45)",
+       "cublas_fp16_plus_relu_tflops": loop(cublas)}
+
+
+def cublas_only():
+    torch.matmul(A, W.t(), out=B)
+
+
+res["cublas_fp16_gemm_only_tflops"] = loop(cublas_only)
 state["a"] = A
 res["engine_pair_tflops"] = loop(make("default"))
 state["a"] = A
