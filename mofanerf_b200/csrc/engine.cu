@@ -35,6 +35,7 @@ int fail(const char* fmt, ...) {
 constexpr int kNShape = 50, kNExp = 30, kNTex = 256, kMultires = 10, kMultiresViews = 4;
 constexpr int kPeXyz = 3 + 6 * kMultires;        // 63
 constexpr int kPeView = 3 + 6 * kMultiresViews;  // 27
+constexpr int kMaxSms = 160;
 constexpr int kHeadStride = 16;                  // fp32 partial-head slots per point: alpha tiles at 0..3, rgb at 4..15
 
 using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -83,6 +84,10 @@ struct Net {
   std::vector<Layer> layers;
   std::vector<Step> program;
   float *w_alpha = nullptr, *b_alpha = nullptr, *w_rgb = nullptr, *b_rgb = nullptr;
+  // fused persistent kernel (W == 256 only): device-resident layer table and weight tensor maps
+  mofa::FusedLayerDesc* fused_layers = nullptr;
+  CUtensorMap* fused_wmaps = nullptr;
+  int fused_n = 0;
   std::vector<void*> allocs;
 };
 
@@ -96,6 +101,7 @@ struct mofa_b200_ctx {
   float* lat[4] = {nullptr, nullptr, nullptr, nullptr};  // device copies of the current latents
   bool latents_set = false;
   bool pair_kernel = true;       // cta_group::2 kernel for N % 256 == 0 (MOFA_B200_DENSE_1CTA=1 disables)
+  bool fused_coarse = true;      // one persistent kernel for a W == 256 net (MOFA_B200_NO_FUSED_COARSE=1 disables)
   int64_t launches = 0;
   // profiling (bench): CUDA-event pairs around every tensor-core dense launch, on the launch stream
   bool profiling = false;
@@ -231,6 +237,7 @@ int fold_net(mofa_b200_ctx* c, Net& net, cudaStream_t s) {
 struct Workspace {
   float *z_c, *w_c, *z_f, *raw, *hp;
   __half *X0, *V, *T[3];
+  __half* fscratch;    // fused coarse kernel: [num_sms * 128, 256] parked skip tensors
   int64_t P_pad;
   size_t total;
 };
@@ -254,6 +261,7 @@ Workspace carve(void* base, int64_t n_chunk, int S_c, int S_f, int Wmax) {
   w.X0 = reinterpret_cast<__half*>(b + take(sizeof(__half) * 64 * w.P_pad));
   w.V = reinterpret_cast<__half*>(b + take(sizeof(__half) * 64 * w.P_pad));
   for (int i = 0; i < 3; ++i) w.T[i] = reinterpret_cast<__half*>(b + take(sizeof(__half) * (size_t)Wmax * w.P_pad));
+  w.fscratch = reinterpret_cast<__half*>(b + take(sizeof(__half) * 256 * 128 * kMaxSms));
   w.total = off;
   return w;
 }
@@ -270,9 +278,46 @@ int run_program(mofa_b200_ctx* c, Net& net, const Workspace& ws, int64_t P_rows,
                 __half* const* act = nullptr) {
   // act != nullptr: training mode — dense step k writes act[k] (kept for the backward pass) instead of the ping-pong buffers
   const int net_id = static_cast<int>(&net - c->nets);
+  (void)net_id;
   const int64_t M = (P_rows + 127) / 128 * 128;
   auto src_ptr = [&](int id) -> __half* { return id == SRC_X0 ? ws.X0 : id == SRC_V ? ws.V : ws.T[id - SRC_T0]; };
   const bool tc = !(flags & MOFA_FLAG_GEMM_SIMT);
+  if (tc && !act && c->fused_coarse && net.fused_n > 0 && c->num_sms <= kMaxSms) {
+    // whole network in one persistent kernel (activations stay in shared memory)
+    FusedLaunch F;
+    memset(&F, 0, sizeof(F));
+    if (make_tmap_2d(c, &F.tmX0, ws.X0, (uint64_t)M, 64, 64, 128)) return 1;
+    if (make_tmap_2d(c, &F.tmV, ws.V, (uint64_t)M, 64, 64, 128)) return 1;
+    if (make_tmap_2d(c, &F.tmScratch, ws.fscratch, (uint64_t)128 * kMaxSms, 256, 256, 128)) return 1;
+    F.wmaps = net.fused_wmaps;
+    F.layers = net.fused_layers;
+    F.n_layers = net.fused_n;
+    F.P_rows = P_rows;
+    F.w_alpha = net.w_alpha; F.b_alpha = net.b_alpha; F.w_rgb = net.w_rgb; F.b_rgb = net.b_rgb;
+    F.raw = ws.raw;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (c->profiling) {
+      const size_t idx = c->recs.size() * 2;
+      while (c->ev.size() < idx + 2) {
+        cudaEvent_t e;
+        CK(cudaEventCreate(&e));
+        c->ev.push_back(e);
+      }
+      e0 = c->ev[idx];
+      e1 = c->ev[idx + 1];
+      CK(cudaEventRecord(e0, s));
+    }
+    CK(launch_coarse_fused(F, c->num_sms, s));
+    if (c->profiling) {
+      double fl = 0.0;
+      for (const Step& st : net.program)
+        if (st.kind == 0) fl += 2.0 * (double)P_rows * (double)net.layers[st.layer].N * (double)net.layers[st.layer].in_ref;
+      CK(cudaEventRecord(e1, s));
+      c->recs.push_back({net_id, fl});
+    }
+    c->launches++;
+    return 0;
+  }
   // head fusion needs every partial slot to fit: W/256 alpha tiles (<= 4), (W/2)/BN rgb tiles (<= 4)
   const int a_tiles = net.W / 256;
   const int r_bn = ((net.W / 2) % 256 == 0) ? 256 : 128;
@@ -388,6 +433,9 @@ int mofa_b200_create(mofa_b200_ctx** out, int device) {
   {
     const char* v = getenv("MOFA_B200_DENSE_1CTA");
     c->pair_kernel = !(v && v[0] == '1');
+    v = getenv("MOFA_B200_NO_FUSED_COARSE");
+    c->fused_coarse = !(v && v[0] == '1');
+    if (e == cudaSuccess) e = mofa::coarse_fused_configure();
   }
   if (e != cudaSuccess) {
     delete c;
@@ -562,6 +610,49 @@ int mofa_b200_load_weights(mofa_b200_ctx* c, int net_id, int W, int D, const flo
       }
     Step st{2, -1, {pb.cur, -1}, -1, 0, {-3, -3}, -1};
     net.program.push_back(st);
+  }
+  if (W == 256) {   // tables for the fused persistent kernel (coarse_fused.cu)
+    std::vector<FusedLayerDesc> fl;
+    std::vector<CUtensorMap> maps;
+    int prev = -1;
+    bool ok = true;
+    for (const Step& st : net.program) {
+      if (st.kind != 0) continue;
+      const Layer& L = net.layers[st.layer];
+      FusedLayerDesc d{};
+      d.bias = L.bias_eff;
+      d.n_out = L.N;
+      d.store = st.head == 2 ? 0 : 1;
+      d.head = st.head;
+      int prim = -1;
+      for (int i = 0; i < L.nseg; ++i)
+        if (st.in_step[i] == prev || (prev == -1 && st.in_step[i] == -1)) prim = i;
+      if (prim < 0) { ok = false; break; }
+      d.kb_prim = L.K[prim] / 64;
+      d.map_prim = static_cast<int>(maps.size());
+      maps.push_back(L.tmB[prim]);
+      if (L.nseg == 2) {
+        const int sec = 1 - prim;
+        d.kb_sec = L.K[sec] / 64;
+        d.sec_kind = st.in_step[sec] == -2 ? 2 : 1;
+        d.map_sec = static_cast<int>(maps.size());
+        maps.push_back(L.tmB[sec]);
+        if (d.sec_kind == 1) {   // mark the producer of the parked tensor
+          if (st.in_step[sec] < 0 || st.in_step[sec] >= (int)fl.size()) { ok = false; break; }
+          fl[st.in_step[sec]].save = 1;
+        }
+      }
+      fl.push_back(d);
+      prev = st.ord;
+    }
+    if (ok) {
+      if (dev_alloc(net, reinterpret_cast<void**>(&net.fused_layers), sizeof(FusedLayerDesc) * fl.size())) return 1;
+      if (dev_alloc(net, reinterpret_cast<void**>(&net.fused_wmaps), sizeof(CUtensorMap) * maps.size())) return 1;
+      CK(cudaMemcpyAsync(net.fused_layers, fl.data(), sizeof(FusedLayerDesc) * fl.size(), cudaMemcpyHostToDevice, s));
+      CK(cudaMemcpyAsync(net.fused_wmaps, maps.data(), sizeof(CUtensorMap) * maps.size(), cudaMemcpyHostToDevice, s));
+      CK(cudaStreamSynchronize(s));   // the host vectors go out of scope
+      net.fused_n = static_cast<int>(fl.size());
+    }
   }
   net.loaded = true;
   if (c->latents_set && fold_net(c, net, s)) return 1;

@@ -83,6 +83,31 @@ cudaError_t launch_copy_f32(const float* src, float* dst, int64_t n, cudaStream_
 cudaError_t launch_finalize_raw(const float* hp, int stride, int a_slot0, int a_tiles, int r_slot0, int r_tiles,
                                 const float* b_alpha, const float* b_rgb, float* raw, int64_t P, cudaStream_t s);
 
+// ---- fused coarse-net kernel (coarse_fused.cu) ---------------------------------------------------
+struct FusedLayerDesc {
+  const float* bias;   // folded bias [n_out]
+  int n_out;           // 256, or 128 for the view layer
+  int kb_prim;         // 64-wide K blocks of the primary A operand (previous layer's output / X0)
+  int kb_sec;          // K blocks of the secondary A operand (0 if none)
+  int sec_kind;        // 1 = parked skip tensor (scratch), 2 = view encoding V
+  int map_prim;        // index into the weight tensor-map array for each segment
+  int map_sec;
+  int store;           // write the activation for the next layer
+  int save;            // also park the activation in the scratch (needed again by a later skip layer)
+  int head;            // 0 none, 1 alpha_linear, 2 rgb_linear (computed in the epilogue)
+};
+struct FusedLaunch {
+  CUtensorMap tmX0, tmV, tmScratch;
+  const CUtensorMap* wmaps;        // device array
+  const FusedLayerDesc* layers;    // device array
+  int n_layers;
+  int64_t P_rows;
+  const float *w_alpha, *b_alpha, *w_rgb, *b_rgb;
+  float* raw;
+};
+cudaError_t launch_coarse_fused(const FusedLaunch& F, int num_sms, cudaStream_t stream);
+cudaError_t coarse_fused_configure();
+
 // ---- backward pass (backward.cu) ----------------------------------------------------------------
 cudaError_t launch_composite_bwd(const float* raw, const float* z, const float* rays, int stride, const float* noise,
                                  const float* d_rgb, const float* d_acc, float gscale, int64_t n, int S,
