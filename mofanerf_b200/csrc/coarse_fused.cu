@@ -30,7 +30,8 @@ struct FusedSmem {
   // barriers: full[3], empty[3], x0_full, sec_full, mma_done[2], act_ready[2][4], tile_done, saved_ready
   static constexpr int N_BARS = 2 * kFusedStages + 2 + 2 + 8 + 2;
   static constexpr int OFF_TPTR = OFF_BAR + N_BARS * 8;
-  static constexpr int TOTAL = OFF_TPTR + 16;
+  static constexpr int OFF_HEAD = OFF_TPTR + 16;               // [128][3] fp32: head partials of epilogue group 1
+  static constexpr int TOTAL = OFF_HEAD + 128 * 3 * 4;
   static constexpr int DYN_BYTES = TOTAL + 1024;
 };
 
@@ -38,7 +39,7 @@ __device__ __forceinline__ void tma_load_2d_g(uint32_t smem_dst, const CUtensorM
   tma_load_2d(smem_dst, tmap, bar, c0, c1);
 }
 
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 coarse_fused_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ CUtensorMap tmV,
                     const __grid_constant__ CUtensorMap tmScratch, const CUtensorMap* __restrict__ wmaps,
                     const FusedLayerDesc* __restrict__ layers, int n_layers, int num_tiles, int64_t P_rows,
@@ -76,7 +77,7 @@ coarse_fused_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_const
     mbar_init(mma_done0, 1);
     mbar_init(mma_done0 + 8, 1);
     for (int i = 0; i < 8; ++i) mbar_init(act_ready0 + 8 * i, 4);   // one arrival per epilogue warp
-    mbar_init(tile_done, 4);
+    mbar_init(tile_done, 8);
     mbar_init(saved_ready, 1);
     fence_mbar_init();
   }
@@ -214,11 +215,15 @@ coarse_fused_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_const
       }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------------ epilogue
-    const int ew = warp - 4;
+    // ------------------------------------------------------------------ epilogue: 8 warps = 2 groups x 4 lane quadrants.
+    // The W=256 layers are epilogue-bound (4 K-blocks of MMA per 128x256 outputs), so two warps per SM sub-partition
+    // split each tile's column blocks: group 0 takes the first half, group 1 the second.
+    const int grp = (warp - 4) >> 2;
+    const int ew = warp & 3;                        // TMEM lane quadrant this warp may read
     const int ep_tid = threadIdx.x - 128;
     const int row = ew * 32 + lane;
     const uint32_t lane_base = static_cast<uint32_t>(ew * 32) << 16;
+    float* head_sh = reinterpret_cast<float*>(base_ptr + L::OFF_HEAD);
     uint32_t done_ph[2] = {0, 0};
     bool pending_save = false;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
@@ -240,8 +245,9 @@ coarse_fused_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_const
         float hacc[3] = {0.f, 0.f, 0.f};
         const float* hw = d.head == 1 ? w_alpha : w_rgb;
         const int hn = d.head == 1 ? 1 : (d.head == 2 ? 3 : 0);
+        const int ncb = d.n_out / 64, half_cb = ncb / 2;
 #pragma unroll 1
-        for (int cb = 0; cb < d.n_out / 64; ++cb) {
+        for (int cb = grp * half_cb; cb < (grp + 1) * half_cb; ++cb) {
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             uint32_t v[32];
@@ -255,27 +261,31 @@ coarse_fused_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_const
               const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
               float f[8];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) f[e] = fminf(fmaxf(__uint_as_float(v[j * 8 + e]) + bb[e], 0.0f), 65504.0f);
+              for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j * 8 + e]) + bb[e];
               if (hn > 0) {
 #pragma unroll
                 for (int q = 0; q < 3; ++q) {
                   if (q >= hn) break;
                   const float4* w4 = reinterpret_cast<const float4*>(hw + q * d.n_out + ncol) + 2 * j;
                   const float4 w0 = __ldg(w4), w1 = __ldg(w4 + 1);
-                  hacc[q] += f[0] * w0.x + f[1] * w0.y + f[2] * w0.z + f[3] * w0.w + f[4] * w1.x + f[5] * w1.y +
-                             f[6] * w1.z + f[7] * w1.w;
+                  hacc[q] += fmaxf(f[0], 0.f) * w0.x + fmaxf(f[1], 0.f) * w0.y + fmaxf(f[2], 0.f) * w0.z +
+                             fmaxf(f[3], 0.f) * w0.w + fmaxf(f[4], 0.f) * w1.x + fmaxf(f[5], 0.f) * w1.y +
+                             fmaxf(f[6], 0.f) * w1.z + fmaxf(f[7], 0.f) * w1.w;
                 }
               }
               if (d.store) {
-                __half2 h0 = __floats2half2_rn(f[0], f[1]);
-                __half2 h1 = __floats2half2_rn(f[2], f[3]);
-                __half2 h2 = __floats2half2_rn(f[4], f[5]);
-                __half2 h3 = __floats2half2_rn(f[6], f[7]);
+                // ReLU + fp16 conversion in one instruction per pair (cvt.rn.relu.f16x2.f32), then a packed
+                // min against the fp16 maximum so that an overflow saturates instead of becoming +inf
+                uint32_t pk[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(pk[e]) : "f"(f[2 * e + 1]), "f"(f[2 * e]));
+                  asm("min.f16x2 %0, %0, %1;" : "+r"(pk[e]) : "r"(0x7bff7bffu));
+                }
                 const int chunk = h * 4 + j;
                 const uint32_t addr = nxt + cb * kKbBytes + row * 128 + ((chunk ^ (row & 7)) << 4);
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
-                             "r"(*reinterpret_cast<uint32_t*>(&h0)), "r"(*reinterpret_cast<uint32_t*>(&h1)),
-                             "r"(*reinterpret_cast<uint32_t*>(&h2)), "r"(*reinterpret_cast<uint32_t*>(&h3))
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]),
+                             "r"(pk[3])
                              : "memory");
               }
             }
@@ -286,16 +296,24 @@ coarse_fused_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_const
             if (lane == 0) mbar_arrive(act_ready0 + 8 * (((l + 1) & 1) * 4 + cb));
           }
         }
-        if (hn > 0 && grow < P_rows) {
-          if (d.head == 1) raw[grow * 4 + 3] = hacc[0] + b_alpha[0];
-          else {
-            raw[grow * 4 + 0] = hacc[0] + b_rgb[0];
-            raw[grow * 4 + 1] = hacc[1] + b_rgb[1];
-            raw[grow * 4 + 2] = hacc[2] + b_rgb[2];
+        if (hn > 0) {                     // combine the two groups' partial dot products (rows are shared, columns split)
+          if (grp == 1) {
+#pragma unroll
+            for (int q = 0; q < 3; ++q) head_sh[row * 3 + q] = hacc[q];
           }
+          named_bar_sync(2, 256);
+          if (grp == 0 && grow < P_rows) {
+            if (d.head == 1) raw[grow * 4 + 3] = hacc[0] + head_sh[row * 3] + b_alpha[0];
+            else {
+              raw[grow * 4 + 0] = hacc[0] + head_sh[row * 3 + 0] + b_rgb[0];
+              raw[grow * 4 + 1] = hacc[1] + head_sh[row * 3 + 1] + b_rgb[1];
+              raw[grow * 4 + 2] = hacc[2] + head_sh[row * 3 + 2] + b_rgb[2];
+            }
+          }
+          named_bar_sync(2, 256);         // head_sh may be rewritten by the next head layer
         }
         if (d.save) {                     // park this layer's output (all 128 rows x 256) for the skip layer
-          named_bar_sync(1, 128);         // every epilogue warp has written + fenced its rows
+          named_bar_sync(1, 256);         // every epilogue warp has written + fenced its rows / columns
           if (ep_tid == 0) {
             for (int kb = 0; kb < 4; ++kb) tma_store_2d(&tmScratch, nxt + kb * kKbBytes, kb * 64, blockIdx.x * 128);
             tma_store_commit();
@@ -321,7 +339,7 @@ cudaError_t launch_coarse_fused(const FusedLaunch& F, int num_sms, cudaStream_t 
   const int num_tiles = static_cast<int>((F.P_rows + 127) / 128);
   if (num_tiles <= 0) return cudaSuccess;
   const int grid = num_tiles < num_sms ? num_tiles : num_sms;
-  coarse_fused_kernel<<<grid, 256, FusedSmem::DYN_BYTES, stream>>>(F.tmX0, F.tmV, F.tmScratch, F.wmaps, F.layers,
+  coarse_fused_kernel<<<grid, 384, FusedSmem::DYN_BYTES, stream>>>(F.tmX0, F.tmV, F.tmScratch, F.wmaps, F.layers,
                                                                   F.n_layers, num_tiles, F.P_rows, F.w_alpha, F.b_alpha,
                                                                   F.w_rgb, F.b_rgb, F.raw);
   return cudaGetLastError();

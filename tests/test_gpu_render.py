@@ -195,8 +195,9 @@ def test_run_network_matches_nerf_forward():
 
 
 def test_training_mode_forward_equals_inference_forward():
-    """With grad-requiring inputs the renderer switches to the activation-keeping forward (fitting); its outputs
-    must equal the inference path bit for bit."""
+    """With grad-requiring inputs the renderer switches to the activation-keeping forward (fitting).  It runs the
+    per-layer kernels where inference runs the fused coarse kernel (different fp32 summation order in the heads), so the
+    maps agree to rounding, not bit for bit: coarse maps 5e-4, final maps 5e-3 (resampling feedback)."""
     from mofanerf_b200 import B200Renderer
     meta, inp, _ = load_case("small_w256")
     c, f, s = build_case_nets(meta)
@@ -209,5 +210,5 @@ def test_training_mode_forward_equals_inference_forward():
         a = r.render_fitting(4, 4, None, shapeCodes=inp["shape"].to(DEV), **args)
     b = r.render_fitting(4, 4, None, shapeCodes=inp["shape"].to(DEV).requires_grad_(True), **args)
     assert b[0].requires_grad and b[0].grad_fn is not None
-    assert torch.equal(a[0], b[0].detach()) and torch.equal(a[2], b[2].detach())
-    assert torch.equal(a[3]["rgb0"], b[3]["rgb0"].detach())
+    assert (a[3]["rgb0"] - b[3]["rgb0"].detach()).abs().max().item() <= 5e-4
+    assert (a[0] - b[0].detach()).abs().max().item() <= 5e-3 and (a[2] - b[2].detach()).abs().max().item() <= 5e-3
