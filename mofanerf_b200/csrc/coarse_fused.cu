@@ -35,6 +35,10 @@ struct FusedSmem {
   static constexpr int DYN_BYTES = TOTAL + 1024;
 };
 
+// The two epilogue groups finish column blocks {0,2} first and {1,3} second; layers with four primary K-blocks consume
+// them in that order (the producer streams the weight K-blocks in the same order).
+__device__ __forceinline__ int kb_order(int i, int kb_prim) { return (kb_prim == 4) ? (((i & 1) << 1) | (i >> 1)) : i; }
+
 __device__ __forceinline__ void tma_load_2d_g(uint32_t smem_dst, const CUtensorMap* tmap, uint32_t bar, int c0, int c1) {
   tma_load_2d(smem_dst, tmap, bar, c0, c1);
 }
@@ -141,7 +145,7 @@ coarse_fused_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_const
           if (elect_one()) {
             const uint32_t fb = full0 + 8 * stage;
             mbar_expect_tx(fb, bytes);
-            if (kb < d.kb_prim) tma_load_2d(ring0 + stage * kRingBytes, wmaps + d.map_prim, fb, kb * 64, 0);
+            if (kb < d.kb_prim) tma_load_2d(ring0 + stage * kRingBytes, wmaps + d.map_prim, fb, kb_order(kb, d.kb_prim) * 64, 0);
             else tma_load_2d(ring0 + stage * kRingBytes, wmaps + d.map_sec, fb, (kb - d.kb_prim) * 64, 0);
           }
           __syncwarp();
@@ -181,6 +185,7 @@ coarse_fused_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_const
         const int nkb = d.kb_prim + d.kb_sec;
         for (int kb = 0; kb < nkb; ++kb) {
           // A operand ready?
+          const int kbp = kb_order(kb, d.kb_prim);     // which K-block of the primary operand this iteration consumes
           if (kb < d.kb_prim) {
             if (l == 0) {
               if (kb == 0) {
@@ -188,7 +193,7 @@ coarse_fused_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_const
                 x0_ph ^= 1u;
               }
             } else {
-              mbar_wait(act_ready0 + 8 * (cur * 4 + kb), ready_ph[cur]);
+              mbar_wait(act_ready0 + 8 * (cur * 4 + kbp), ready_ph[cur]);
             }
           } else if (kb == d.kb_prim) {
             mbar_wait(sec_full, sec_ph);
@@ -196,7 +201,7 @@ coarse_fused_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_const
           }
           mbar_wait(full0 + 8 * stage, phase);
           tc_fence_after();
-          const uint32_t a_addr = (kb < d.kb_prim) ? a_prim + kb * kKbBytes : a_sec + (kb - d.kb_prim) * kKbBytes;
+          const uint32_t a_addr = (kb < d.kb_prim) ? a_prim + kbp * kKbBytes : a_sec + (kb - d.kb_prim) * kKbBytes;
           const uint64_t da = umma_desc_sw128_kmajor(a_addr);
           const uint64_t db = umma_desc_sw128_kmajor(ring0 + stage * kRingBytes);
           if (elect_one()) {
@@ -250,6 +255,8 @@ coarse_fused_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_const
         for (int cb = grp * half_cb; cb < (grp + 1) * half_cb; ++cb) {
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
+            // (no software pipelining of tcgen05.ld: the destination registers of an in-flight load must not be touched
+            //  by the compiler, which cannot be guaranteed across this much unrolled code — tried, produced wrong data)
             uint32_t v[32];
             tmem_ld_32x32b_x32(tmem_base + lane_base + acc * 256 + cb * 64 + h * 32, v);
             tmem_ld_wait();
