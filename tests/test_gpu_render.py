@@ -69,7 +69,10 @@ def check_maps(name, got, ref, max_rgb=6e-2, mean_rgb=3e-3, min_psnr=40.0, max_a
     for k, ka in (("disp_map", "acc_map"), ("disp0", "acc0")):
         if k in ref:
             empty = ref[ka] == 0
-            assert bool(torch.isnan(got[k][empty]).all()), f"{name} {k}: NaN expected where acc == 0"
+            # NaN disparity (0/0) wherever BOTH see no density at all; a ray the reference renders as exactly empty may
+            # pick up a ~1e-6 weight in the fp16 chain (sigma + noise crossing zero): then acc must stay negligible
+            assert bool(torch.isnan(got[k][empty & (got[ka] == 0)]).all()), f"{name} {k}: NaN expected where acc == 0"
+            assert bool((got[ka][empty] <= 1e-3).all()), f"{name} {ka}: density where the reference has none"
             solid = (ref[ka] > disp_min_acc) & (got[ka] > disp_min_acc)
             if solid.any():
                 rel = ((got[k][solid] - ref[k][solid]).abs() / ref[k][solid].abs().clamp_min(1e-6)).max().item()
