@@ -39,10 +39,6 @@ struct FusedSmem {
 // them in that order (the producer streams the weight K-blocks in the same order).
 __device__ __forceinline__ int kb_order(int i, int kb_prim) { return (kb_prim == 4) ? (((i & 1) << 1) | (i >> 1)) : i; }
 
-__device__ __forceinline__ void tma_load_2d_g(uint32_t smem_dst, const CUtensorMap* tmap, uint32_t bar, int c0, int c1) {
-  tma_load_2d(smem_dst, tmap, bar, c0, c1);
-}
-
 __global__ void __launch_bounds__(384, 1)
 coarse_fused_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ CUtensorMap tmV,
                     const __grid_constant__ CUtensorMap tmScratch, const CUtensorMap* __restrict__ wmaps,
@@ -131,12 +127,7 @@ coarse_fused_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_const
           }
           __syncwarp();
         }
-        if (l > 0) {   // keep the per-accumulator phase counters in step with the MMA warp: one completion per layer
-          const int a = (l - 1) & 1;
-          if (d.kb_sec == 0) { /* not waited above */ }
-          done_ph[a] ^= 1u;
-          (void)a;
-        }
+        if (l > 0) done_ph[(l - 1) & 1] ^= 1u;   // one completion of mma_done[(l-1)&1] per layer, waited for or not
         // weight K-blocks of this layer: primary segment then secondary
         const int nkb = d.kb_prim + d.kb_sec;
         const uint32_t bytes = d.n_out * 128;

@@ -47,11 +47,6 @@ cudaError_t launch_dense_tc2(const DenseLaunch& L, int num_sms, cudaStream_t str
 cudaError_t dense_tc2_configure();
 
 // ---- element-wise / per-ray kernels (sampling.cu) -----------------------------------------------
-struct RayView {
-  const float* rays;   // [n, stride]
-  int stride;
-};
-
 cudaError_t launch_zvals_coarse(const float* rays, int stride, int64_t n, int S, int lindisp, float perturb,
                                 const float* t_rand, uint64_t seed, int64_t ray_offset, float* z,
                                 cudaStream_t s);
