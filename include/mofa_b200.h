@@ -147,6 +147,13 @@ typedef struct mofa_b200_bwd_args {
   float* d_shape;            /* [50]  out */
   float* d_expmod;           /* [30]  out: w.r.t. the modulated expression code passed to set_latents */
   float* d_tex;              /* [256] out */
+  /* optional (training): fp32 gradient buffers for the network parameters, in the (weight, bias) order
+   * of mofa_b200_load_weights and with the reference tensors' shapes; must be zero-initialised by the caller; gradients
+   * are ACCUMULATED into them.  NULL = weights are constants (fitting). */
+  float* const* d_params_coarse;
+  float* const* d_params_fine;
+  int32_t n_params_coarse;
+  int32_t n_params_fine;
   void* workspace;
   size_t workspace_bytes;
 } mofa_b200_bwd_args;
@@ -178,6 +185,12 @@ int mofa_b200_sample_pdf_merge(mofa_b200_ctx* ctx, const float* z, const float* 
 int mofa_b200_raw2outputs_bwd(mofa_b200_ctx* ctx, const float* raw, const float* z, const float* rays, int stride,
                               const float* noise, const float* d_rgb, const float* d_acc, int64_t n, int S,
                               int white_bkgd, float* d_raw, float* d_rays, void* stream);
+
+/* The weight-gradient contraction as the engine runs it: C[Mp, ldc] (+)= scale * A^T · B with A [P, Mp], B [P, Kb] fp16
+ * row-major and the reduction over the P rows (both operands MN-major for the tensor core); columns >= n_valid are not
+ * written.  Mp % 128 == 0, Kb % 64 == 0, P % 64 == 0.  use_simt selects the verification kernel. */
+int mofa_b200_wgrad(mofa_b200_ctx* ctx, const void* A, int Mp, const void* B, int Kb, int n_valid, int64_t P, float scale,
+                    float* C, int ldc, int use_simt, void* stream);
 
 /* One dense layer as the engine runs it: C[M,N] = act(A0[M,K0]·B0[N,K0]^T (+ A1[M,K1]·B1[N,K1]^T) + bias).
  * fp16 operands (device, row-major, K0/K1 multiples of 64, N multiple of 128, M multiple of 128),

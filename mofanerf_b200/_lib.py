@@ -40,6 +40,8 @@ class BwdArgs(C.Structure):
         ("d_rgb", C.c_void_p), ("d_acc", C.c_void_p), ("d_rgb0", C.c_void_p), ("d_acc0", C.c_void_p),
         ("loss_scale", C.c_float), ("reserved_f", C.c_float),
         ("d_rays", C.c_void_p), ("d_shape", C.c_void_p), ("d_expmod", C.c_void_p), ("d_tex", C.c_void_p),
+        ("d_params_coarse", C.c_void_p), ("d_params_fine", C.c_void_p),
+        ("n_params_coarse", C.c_int32), ("n_params_fine", C.c_int32),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
     ]
 
@@ -72,6 +74,8 @@ SIGNATURES = {
                                             C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mofa_b200_sample_pdf_merge": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
                                              C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mofa_b200_wgrad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_float, C.c_void_p,
+                                  C.c_int, C.c_int, C.c_void_p]),
     "mofa_b200_dense": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                   C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "mofa_b200_launch_count": (C.c_int64, [C.c_void_p]),

@@ -2,7 +2,9 @@
 
 Differentiable: the packed ray batch [N,11] (so pose / ray origins / directions / view directions, through
 whatever PyTorch graph built it), the shape code, the modulated expression code and the texture code.
-Constants: network weights (run_fit.py does not optimise them), sample depths (the reference detaches
+Network weights: constants for fitting (run_fit.py does not optimise them: the nets are in eval() mode there); when the
+nets are in train() mode (run_train.py) their parameters are passed as extra inputs and receive gradients (f2).
+Constants: sample depths (the reference detaches
 z_samples, models/render_class.py:326).  disp_map / z_std are returned as non-differentiable.
 """
 from __future__ import annotations
@@ -14,7 +16,7 @@ import torch
 
 class RenderRaysFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, rays, shape, exp_mod, tex, engine, cfg):
+    def forward(ctx, rays, shape, exp_mod, tex, engine, cfg, *params):
         engine.set_latents(shape, exp_mod, tex)
         out = engine.render_rays(rays.detach(), cfg["N_samples"], cfg["N_importance"], run_fine=cfg["run_fine"],
                                  fine_net=cfg["fine_net"], perturb=cfg["perturb"], raw_noise_std=cfg["raw_noise_std"],
@@ -24,6 +26,8 @@ class RenderRaysFn(torch.autograd.Function):
         if cfg["raw_noise_std"] > 0 and cfg.get("noise_c") is None:
             raise NotImplementedError("training-mode render with in-kernel sigma noise: pass explicit noise tensors")
         ctx.engine, ctx.cfg = engine, cfg
+        ctx.param_shapes = [tuple(p.shape) for p in params]
+        ctx.n_coarse = cfg.get("n_params_coarse", 0)
         ctx.saved = {k: out.pop(k) for k in ("_train_ws", "_rays", "_noise")}
         ctx.fine = "rgb0" in out
         keys = ["rgb_map", "acc_map", "disp_map"] + (["rgb0", "acc0", "disp0", "z_std"] if ctx.fine else [])
@@ -44,9 +48,16 @@ class RenderRaysFn(torch.autograd.Function):
         scale = 2.0 ** round(math.log2(8192.0 / amax)) if amax > 0 else 1.0
         scale = min(max(scale, 2.0 ** -20), 2.0 ** 40)
         cfg = ctx.cfg
+        grads_p, pg = [], None
+        if ctx.param_shapes:      # training: weight gradients of the coarse (and fine) network, canonical order
+            dev = ctx.saved["_rays"].device
+            grads_p = [torch.zeros(s, dtype=torch.float32, device=dev) for s in ctx.param_shapes]
+            nc = ctx.n_coarse
+            pg = (grads_p[:nc], grads_p[nc:] if len(grads_p) > nc else None)
         d_rays, d_shape, d_exp, d_tex = ctx.engine.render_rays_bwd(
             ctx.saved, cfg["N_samples"], cfg["N_importance"], run_fine=cfg["run_fine"], fine_net=cfg["fine_net"],
             white_bkgd=cfg["white_bkgd"], lindisp=cfg["lindisp"], d_rgb=d_rgb, d_acc=d_acc,
-            d_rgb0=d_rgb0 if ctx.fine else None, d_acc0=d_acc0 if ctx.fine else None, loss_scale=scale)
+            d_rgb0=d_rgb0 if ctx.fine else None, d_acc0=d_acc0 if ctx.fine else None, loss_scale=scale,
+            param_grads=pg)
         ctx.saved = None   # release the activation workspace
-        return d_rays, d_shape, d_exp, d_tex, None, None
+        return (d_rays, d_shape, d_exp, d_tex, None, None) + tuple(grads_p)

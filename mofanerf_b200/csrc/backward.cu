@@ -277,6 +277,67 @@ cudaError_t launch_pack_weight_t(const float* src, int ld, int c0, int K, int kr
   return cudaGetLastError();
 }
 
+// y[i] += a * x[i]
+__global__ void axpy_f32_kernel(const float* __restrict__ x, float a, float* __restrict__ y, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] += a * x[i];
+}
+cudaError_t launch_axpy_f32(const float* x, float a, float* y, int n, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  axpy_f32_kernel<<<(n + 255) / 256, 256, 0, s>>>(x, a, y, n);
+  return cudaGetLastError();
+}
+
+// G[r * ld + c0 + j] += a * u[r] * v[j]      (latent columns of a folded layer: d bias (x) latent)
+__global__ void outer_add_kernel(const float* __restrict__ u, const float* __restrict__ v, int rows, int cols, float a,
+                                 float* __restrict__ G, int ld, int c0) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * cols) return;
+  const int r = i / cols, j = i % cols;
+  G[static_cast<size_t>(r) * ld + c0 + j] += a * u[r] * v[j];
+}
+cudaError_t launch_outer_add(const float* u, const float* v, int rows, int cols, float a, float* G, int ld, int c0,
+                             cudaStream_t s) {
+  const int tot = rows * cols;
+  if (tot == 0) return cudaSuccess;
+  outer_add_kernel<<<(tot + 255) / 256, 256, 0, s>>>(u, v, rows, cols, a, G, ld, c0);
+  return cudaGetLastError();
+}
+
+// Head weight gradients: gW[q, c] += a * sum_p g[p*4 + q0 + q] * act[p, c];  gb[q] += a * sum_p g[p*4 + q0 + q]
+// grid (N/64, row blocks of 2048); 256 threads = 64 columns x 4 row phases
+__global__ void head_wgrad_kernel(const float* __restrict__ g, int q0, int nq, const __half* __restrict__ act, int N,
+                                  int64_t P, float a, float* __restrict__ gW, float* __restrict__ gb) {
+  __shared__ float red[4][3][64];
+  const int c = threadIdx.x & 63, ph = threadIdx.x >> 6;
+  const int col = blockIdx.x * 64 + c;
+  const int64_t r0 = static_cast<int64_t>(blockIdx.y) * 2048;
+  const int64_t r1 = (r0 + 2048 < P) ? r0 + 2048 : P;
+  float acc[3] = {0.f, 0.f, 0.f}, accb[3] = {0.f, 0.f, 0.f};
+  for (int64_t r = r0 + ph; r < r1; r += 4) {
+    const float x = __half2float(act[r * N + col]);
+    for (int q = 0; q < nq; ++q) {
+      const float gq = g[r * 4 + q0 + q];
+      acc[q] += gq * x;
+      accb[q] += gq;
+    }
+  }
+  for (int q = 0; q < 3; ++q) red[ph][q][c] = acc[q];
+  __syncthreads();
+  if (ph == 0)
+    for (int q = 0; q < nq; ++q)
+      atomicAdd(gW + static_cast<size_t>(q) * N + col, a * (red[0][q][c] + red[1][q][c] + red[2][q][c] + red[3][q][c]));
+  if (blockIdx.x == 0 && c == 0)   // bias: every row phase of the first column block adds its partial
+    for (int q = 0; q < nq; ++q) atomicAdd(gb + q, a * accb[q]);
+}
+cudaError_t launch_head_wgrad(const float* g, int q0, int nq, const __half* act, int N, int64_t P, float a, float* gW,
+                              float* gb, cudaStream_t s) {
+  if (P == 0) return cudaSuccess;
+  dim3 grid(N / 64, static_cast<unsigned>((P + 2047) / 2048));
+  head_wgrad_kernel<<<grid, 256, 0, s>>>(g, q0, nq, act, N, P, a, gW, gb);
+  return cudaGetLastError();
+}
+
 __global__ void scale_f32_kernel(float* __restrict__ x, float a, int64_t n) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < n) x[i] *= a;

@@ -61,6 +61,9 @@ struct Layer {
   int in_ref = 0;                // reference in_features (algorithmic FLOP accounting)
   // backward: transposed segment weights [rows_t, N] (rows_t = K padded to >= 128), the
   // K-major B operand of dX = dZ · W
+  int seg_c0[2] = {0, 0};        // first column / real width of each activation segment in the reference weight
+  int seg_kreal[2] = {0, 0};
+  int fold_c0 = 0;               // first latent column
   __half* wt[2] = {nullptr, nullptr};
   int rows_t[2] = {0, 0};
   int BN_t[2] = {256, 256};
@@ -164,6 +167,8 @@ int build_layer(mofa_b200_ctx* c, Net& net, const LayerSpec& sp, const float* w,
   if (sp.N % L.BN != 0) return fail("layer width %d is not a multiple of 128", sp.N);
   for (int i = 0; i < sp.nseg; ++i) {
     L.K[i] = sp.seg_kpad[i];
+    L.seg_c0[i] = sp.seg_c0[i];
+    L.seg_kreal[i] = sp.seg_k[i];
     if (dev_alloc(net, reinterpret_cast<void**>(&L.w[i]), sizeof(__half) * (size_t)sp.N * L.K[i])) return 1;
     CK(launch_pack_weight(w, sp.in_total, sp.seg_c0[i], sp.seg_k[i], L.K[i], sp.N, L.w[i], s));
     c->launches++;
@@ -183,6 +188,7 @@ int build_layer(mofa_b200_ctx* c, Net& net, const LayerSpec& sp, const float* w,
   if (sp.fold_n > 0) {
     L.fold_n = sp.fold_n;
     L.fold_lat = sp.fold_lat;
+    L.fold_c0 = sp.fold_c0;
     if (dev_alloc(net, reinterpret_cast<void**>(&L.fold_w), sizeof(float) * (size_t)sp.N * sp.fold_n)) return 1;
     CK(cudaMemcpy2DAsync(L.fold_w, sizeof(float) * sp.fold_n, w + sp.fold_c0, sizeof(float) * sp.in_total,
                          sizeof(float) * sp.fold_n, sp.N, cudaMemcpyDeviceToDevice, s));
@@ -436,6 +442,7 @@ int mofa_b200_create(mofa_b200_ctx** out, int device) {
     v = getenv("MOFA_B200_NO_FUSED_COARSE");
     c->fused_coarse = !(v && v[0] == '1');
     if (e == cudaSuccess) e = mofa::coarse_fused_configure();
+    if (e == cudaSuccess) e = mofa::wgrad_configure();
   }
   if (e != cudaSuccess) {
     delete c;
@@ -885,6 +892,7 @@ namespace {
 
 struct PassBufs {
   float *z, *raw;                 // [n,S], [P,4]
+  __half *X0, *V;                 // [P,64] encodings (kept for the weight gradients of the first / view layer)
   std::vector<__half*> act;       // per dense step: [P_pad, N]
 };
 
@@ -924,6 +932,8 @@ TrainWS carve_train(void* base, int64_t n, int S_c, int S_f, const Net& nc, cons
     const int S = ps == 0 ? S_c : S_f;
     t.pass[ps].z = reinterpret_cast<float*>(take(sizeof(float) * n * S));
     t.pass[ps].raw = reinterpret_cast<float*>(take(sizeof(float) * 4 * P));
+    t.pass[ps].X0 = reinterpret_cast<__half*>(take(sizeof(__half) * 64 * P));
+    t.pass[ps].V = reinterpret_cast<__half*>(take(sizeof(__half) * 64 * P));
     for (const Step& st : net->program)
       if (st.kind == 0)
         t.pass[ps].act.push_back(reinterpret_cast<__half*>(take(sizeof(__half) * (size_t)P * net->layers[st.layer].N)));
@@ -941,8 +951,9 @@ TrainWS carve_train(void* base, int64_t n, int S_c, int S_f, const Net& nc, cons
 }
 
 // Backward of one pass through `net`: d_raw (loss-scaled) -> dX0/dV and latent gradients.
+// d_params (optional): fp32 gradient buffers in the canonical (weight, bias) order of mofa_b200_load_weights
 int run_backward(mofa_b200_ctx* c, Net& net, const TrainWS& t, const PassBufs& pb, int64_t P_rows, float inv_scale,
-                 float* const d_lat[4], cudaStream_t s) {
+                 float* const d_lat[4], float* const* d_params, cudaStream_t s) {
   const int64_t M = (P_rows + 127) / 128 * 128;
   std::vector<const Step*> dense;
   for (const Step& st : net.program)
@@ -1000,12 +1011,53 @@ int run_backward(mofa_b200_ctx* c, Net& net, const TrainWS& t, const PassBufs& p
     } else {
       if (gemm(k, L.N, t.dz[k], pb.act[k], st.head == 1)) return 1;
     }
-    if (L.fold_n > 0) {   // adjoint of the latent fold: d(bias_eff) = column sums of dZ
+    if (L.fold_n > 0 || d_params) {   // d(bias_eff) = column sums of dZ (adjoint of the latent fold; bias gradient)
       CK(cudaMemsetAsync(t.d_beff, 0, sizeof(float) * L.N, s));
       CK(launch_colsum(t.dz[k], L.N, P_rows, t.d_beff, s));
+      c->launches++;
+    }
+    if (L.fold_n > 0) {
       CK(launch_fold_bwd(L.fold_w, L.fold_n, L.N, t.d_beff, inv_scale, d_lat[L.fold_lat], s));
+      c->launches++;
+    }
+    if (d_params) {   // weight gradients: dW_seg += dZ^T · X_seg, db += colsum(dZ), latent columns += db (x) latent
+      float* gW = d_params[2 * st.layer];
+      float* gb = d_params[2 * st.layer + 1];
+      CK(launch_axpy_f32(t.d_beff, inv_scale, gb, L.N, s));
+      if (L.fold_n > 0)
+        CK(launch_outer_add(t.d_beff, c->lat[L.fold_lat], L.N, L.fold_n, inv_scale, gW, L.in_ref, L.fold_c0, s));
+      for (int i = 0; i < L.nseg; ++i) {
+        const __half* X = st.in_step[i] >= 0 ? pb.act[st.in_step[i]] : (st.in_step[i] == -1 ? pb.X0 : pb.V);
+        WgradLaunch W;
+        memset(&W, 0, sizeof(W));
+        if (make_tmap_2d(c, &W.tmA, t.dz[k], (uint64_t)M, (uint64_t)L.N, (uint64_t)L.N, 64)) return 1;
+        if (make_tmap_2d(c, &W.tmB, X, (uint64_t)M, (uint64_t)L.K[i], (uint64_t)L.K[i], 64)) return 1;
+        W.C = gW + L.seg_c0[i];
+        W.ldc = L.in_ref;
+        W.n_valid = L.seg_kreal[i];
+        W.scale = inv_scale;
+        W.Mp = L.N;
+        W.BN = (L.K[i] % 256 == 0) ? 256 : 128;
+        W.Np = (L.K[i] + W.BN - 1) / W.BN * W.BN;
+        W.P = M;
+        CK(launch_wgrad_tc(W, c->num_sms, s));
+        c->launches++;
+      }
       c->launches += 2;
     }
+  }
+  if (d_params) {   // heads: alpha_linear (W -> 1) on sigmaCodes, rgb_linear (W/2 -> 3) on the view layer's activation
+    const int n_dense = nd;
+    for (int k = 0; k < nd; ++k) {
+      const Step& st = *dense[k];
+      if (st.head == 1)
+        CK(launch_head_wgrad(t.d_raw, 3, 1, pb.act[k], net.W, P_rows, inv_scale, d_params[2 * (n_dense + 0)],
+                             d_params[2 * (n_dense + 0) + 1], s));
+      else if (st.head == 2)
+        CK(launch_head_wgrad(t.d_raw, 0, 3, pb.act[k], net.W / 2, P_rows, inv_scale, d_params[2 * (n_dense + 1)],
+                             d_params[2 * (n_dense + 1) + 1], s));
+    }
+    c->launches += 2;
   }
   if (gemm(-1, 128, t.dX0, nullptr, false)) return 1;
   if (gemm(-2, 128, t.dV, nullptr, false)) return 1;
@@ -1053,6 +1105,8 @@ int mofa_b200_render_rays_train_fwd(mofa_b200_ctx* c, const mofa_b200_render_arg
   const int white = (a->flags & MOFA_FLAG_WHITE_BKGD) ? 1 : 0;
   Workspace ws = t.fw;
   // ---- coarse pass (activations kept)
+  ws.X0 = t.pass[0].X0;
+  ws.V = t.pass[0].V;
   CK(launch_zvals_coarse(a->rays, a->ray_stride, n, S_c, lindisp, a->perturb, a->t_rand, a->seed, 0, t.pass[0].z, s));
   CK(launch_encode_rays(a->rays, a->ray_stride, t.pass[0].z, n, S_c, kMultires, kMultiresViews, ws.X0, ws.V, s));
   c->launches += 2;
@@ -1067,6 +1121,8 @@ int mofa_b200_render_rays_train_fwd(mofa_b200_ctx* c, const mofa_b200_render_arg
   if (fine) {
     const int det = (a->perturb == 0.0f) ? 1 : 0;
     CK(launch_sample_pdf_merge(t.pass[0].z, ws.w_c, a->u, det, a->seed, 0, n, S_c, N_i, nullptr, t.pass[1].z, a->z_std, s));
+    ws.X0 = t.pass[1].X0;
+    ws.V = t.pass[1].V;
     CK(launch_encode_rays(a->rays, a->ray_stride, t.pass[1].z, n, S_f, kMultires, kMultiresViews, ws.X0, ws.V, s));
     c->launches += 2;
     ws.raw = t.pass[1].raw;
@@ -1123,7 +1179,10 @@ int mofa_b200_render_rays_bwd(mofa_b200_ctx* c, const mofa_b200_bwd_args* a, voi
     CK(launch_composite_bwd(t.pass[ps].raw, t.pass[ps].z, a->rays, a->ray_stride, noise, g_rgb, g_acc, scale, n, S, white,
                             t.d_raw, a->d_rays, s));
     c->launches++;
-    if (run_backward(c, net, t, t.pass[ps], n * S, inv, d_lat, s)) return 1;
+    float* const* dp = (&net == &nc) ? a->d_params_coarse : a->d_params_fine;
+    if (dp && (&net == &nc ? a->n_params_coarse : a->n_params_fine) != 2 * (n_dense_steps(net) + 2))
+      return fail("bwd: d_params has the wrong number of tensors");
+    if (run_backward(c, net, t, t.pass[ps], n * S, inv, d_lat, dp, s)) return 1;
     CK(launch_pe_bwd(a->rays, a->ray_stride, t.pass[ps].z, t.dX0, t.dV, 128, n, S, a->d_rays, s));
     c->launches++;
   }
@@ -1141,6 +1200,29 @@ int mofa_b200_raw2outputs_bwd(mofa_b200_ctx* c, const float* raw, const float* z
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   CK(cudaMemsetAsync(d_rays, 0, sizeof(float) * 11 * n, s));
   CK(launch_composite_bwd(raw, z, rays, stride, noise, d_rgb, d_acc, 1.0f, n, S, white_bkgd, d_raw, d_rays, s));
+  c->launches++;
+  return 0;
+}
+
+int mofa_b200_wgrad(mofa_b200_ctx* c, const void* A, int Mp, const void* B, int Kb, int n_valid, int64_t P, float scale,
+                    float* C, int ldc, int use_simt, void* stream) {
+  if (!c) return fail("wgrad: ctx is NULL");
+  if (Mp % 128 != 0 || Kb % 64 != 0 || P % 64 != 0) return fail("wgrad: Mp%%128, Kb%%64, P%%64 required");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (use_simt) {
+    CK(launch_wgrad_simt(static_cast<const __half*>(A), Mp, static_cast<const __half*>(B), Kb, P, Mp, n_valid, scale, C, ldc, s));
+  } else {
+    WgradLaunch W;
+    memset(&W, 0, sizeof(W));
+    if (make_tmap_2d(c, &W.tmA, A, (uint64_t)P, (uint64_t)Mp, (uint64_t)Mp, 64)) return 1;
+    if (make_tmap_2d(c, &W.tmB, B, (uint64_t)P, (uint64_t)Kb, (uint64_t)Kb, 64)) return 1;
+    W.C = C; W.ldc = ldc; W.n_valid = n_valid; W.scale = scale; W.Mp = Mp;
+    W.BN = (Kb % 256 == 0) ? 256 : 128;
+    W.Np = (Kb + W.BN - 1) / W.BN * W.BN;
+    W.P = P;
+    CK(launch_wgrad_tc(W, c->num_sms, s));
+  }
   c->launches++;
   return 0;
 }

@@ -117,5 +117,28 @@ cudaError_t launch_pe_bwd(const float* rays, int stride, const float* z, const _
 cudaError_t launch_pack_weight_t(const float* src, int ld, int c0, int K, int krows_pad, int N, __half* dst,
                                  cudaStream_t s);
 cudaError_t launch_scale_f32(float* x, float a, int64_t n, cudaStream_t s);
+cudaError_t launch_axpy_f32(const float* x, float a, float* y, int n, cudaStream_t s);
+cudaError_t launch_outer_add(const float* u, const float* v, int rows, int cols, float a, float* G, int ld, int c0,
+                             cudaStream_t s);
+cudaError_t launch_head_wgrad(const float* g, int q0, int nq, const __half* act, int N, int64_t P, float a, float* gW,
+                              float* gb, cudaStream_t s);
+
+// ---- weight-gradient GEMM (dense_wgrad.cu): C[Mp, :] += scale * A^T B, reduction over the P rows of A [P,Mp], B [P,Np]
+struct WgradLaunch {
+  CUtensorMap tmA;   // [P, Mp] fp16, box {64 cols, 64 rows}, SWIZZLE_128B
+  CUtensorMap tmB;   // [P, cols of B] fp16, same box
+  float* C;          // fp32, already offset to the first output column
+  int ldc;
+  int n_valid;       // real columns of B
+  float scale;
+  int Mp;            // multiple of 128
+  int Np;            // multiple of BN (columns beyond the tensor are zero-filled by TMA)
+  int BN;            // 128 or 256
+  int64_t P;         // multiple of 64
+};
+cudaError_t launch_wgrad_tc(const WgradLaunch& W, int num_sms, cudaStream_t stream);
+cudaError_t wgrad_configure();
+cudaError_t launch_wgrad_simt(const __half* A, int lda, const __half* B, int ldb, int64_t P, int Mp, int n_valid,
+                              float scale, float* C, int ldc, cudaStream_t stream);
 
 }  // namespace mofa

@@ -179,8 +179,10 @@ class Engine:
 
     def render_rays_bwd(self, saved: Dict[str, torch.Tensor], N_samples: int, N_importance: int, *, run_fine: bool,
                         fine_net: int, white_bkgd: bool, lindisp: bool, d_rgb=None, d_acc=None, d_rgb0=None,
-                        d_acc0=None, loss_scale: float = 1.0):
-        """Backward of a training-mode render_rays: returns (d_rays [n,11], d_shape [50], d_expmod [30], d_tex [256])."""
+                        d_acc0=None, loss_scale: float = 1.0, param_grads=None):
+        """Backward of a training-mode render_rays: returns (d_rays [n,11], d_shape [50], d_expmod [30], d_tex [256]).
+        param_grads: optional (coarse_list, fine_list) of zero-initialised fp32 tensors shaped like the canonical
+        (weight, bias) parameter lists; weight gradients are accumulated into them (training)."""
         rays, ws = saved["_rays"], saved["_train_ws"]
         noise_c, noise_f = saved["_noise"]
         dev, n = self.device, rays.shape[0]
@@ -199,6 +201,15 @@ class Engine:
             a.d_rgb, a.d_acc, a.d_rgb0, a.d_acc0 = [_ptr(x) for x in g]
             a.loss_scale = float(loss_scale)
             a.d_rays, a.d_shape, a.d_expmod, a.d_tex = d_rays.data_ptr(), d_shape.data_ptr(), d_exp.data_ptr(), d_tex.data_ptr()
+            keep = []
+            if param_grads is not None:
+                for name, lst in (("coarse", param_grads[0]), ("fine", param_grads[1])):
+                    if lst is None:
+                        continue
+                    arr = (C.c_void_p * len(lst))(*[t.data_ptr() for t in lst])
+                    keep.append(arr)
+                    setattr(a, f"d_params_{name}", C.cast(arr, C.c_void_p))
+                    setattr(a, f"n_params_{name}", len(lst))
             a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
             _lib.check(self.lib.mofa_b200_render_rays_bwd(self._h, C.byref(a), self._stream()))
         self._keep["bwd"] = g
@@ -266,6 +277,19 @@ class Engine:
                                                            N_importance, zs.data_ptr(), zm.data_ptr(), sd.data_ptr(),
                                                            self._stream()))
         return zs, zm, sd
+
+    def wgrad(self, dZ, X, n_valid=None, scale=1.0, simt=False):
+        """C = scale * dZ^T · X  (fp16 operands [P, M'] and [P, K], fp32 result [M', n_valid]) — the weight-gradient GEMM."""
+        dZ = dZ.to(self.device, torch.float16).contiguous()
+        X = X.to(self.device, torch.float16).contiguous()
+        P, Mp = dZ.shape
+        Kb = X.shape[1]
+        n_valid = Kb if n_valid is None else n_valid
+        out = torch.zeros(Mp, n_valid, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.mofa_b200_wgrad(self._h, dZ.data_ptr(), Mp, X.data_ptr(), Kb, n_valid, P, float(scale),
+                                                out.data_ptr(), n_valid, int(simt), self._stream()))
+        return out
 
     def dense(self, A0, B0, bias=None, A1=None, B1=None, relu=True, simt=False, mode=None):
         """C = act(A0·B0^T (+ A1·B1^T) + bias) with fp16 operands.

@@ -171,10 +171,10 @@ class B200Renderer(torch.nn.Module):
                    noise_f=noise_f, want_aux=want_aux)
         if needs_grad:
             # fitting (run_fit.py:305-313): gradients w.r.t. rays (pose) and the three codes; weights are constants
-            if not B200Renderer._warned_weights:
+            if not B200Renderer._warned_weights and not getattr(network_fn, "module", network_fn).training:
                 B200Renderer._warned_weights = True
-                warnings.warn("mofanerf_b200: autograd through render_rays propagates to rays (pose) and the shape / texture / "
-                              "expression codes; gradients w.r.t. the NeRF weights are not computed (SURVEY.md §8 row f2)")
+                warnings.warn("mofanerf_b200: networks are in eval() mode: gradients flow to rays (pose) and the shape / "
+                              "texture / expression codes only; put the networks in train() mode for weight gradients")
             if gemm_simt:
                 raise NotImplementedError("the SIMT verification kernel has no training mode")
             from .autograd import RenderRaysFn
@@ -189,7 +189,20 @@ class B200Renderer(torch.nn.Module):
             shape = self.shapeCodes[0, :].reshape(-1).to(rays.device)
             exp_mod = self._exp_mod().reshape(-1).to(rays.device)
             tex = self.decoding_texCodes.reshape(-1).to(rays.device)
-            outs = RenderRaysFn.apply(rays, shape, exp_mod, tex, eng, cfg)
+            # weight gradients (run_train.py) only when the networks are in train() mode: render_fitting() puts them in
+            # eval() (models/render_class.py:383-384) and run_fit.py never optimises them
+            params = []
+            from .nets import canonical_tensors
+            mods = [network_fn] + ([network_fine] if (network_fine is not None and fine) else [])
+            if all(getattr(m, "module", m).training for m in mods) and torch.is_grad_enabled():
+                pc = canonical_tensors(network_fn)[0]
+                params = list(pc)
+                cfg["n_params_coarse"] = len(pc)
+                if len(mods) > 1:
+                    params += list(canonical_tensors(network_fine)[0])
+                if not all(p.requires_grad for p in params):
+                    params = []
+            outs = RenderRaysFn.apply(rays, shape, exp_mod, tex, eng, cfg, *params)
             keys = ["rgb_map", "acc_map", "disp_map"] + (["rgb0", "acc0", "disp0", "z_std"] if fine else [])
             keys += [k for k in (("raw",) if retraw else ()) + (("weights", "z_vals") if want_aux else ())]
             return dict(zip(keys, outs))
