@@ -49,7 +49,7 @@ def parse():
     ap.add_argument("--chunk-rays", type=int, default=0, help="engine-internal rays per pass (0 = default)")
     ap.add_argument("--cpu-sample-rays", type=int, default=0, help="rays in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="frame", choices=["frame", "fit"],
+    ap.add_argument("--workload", default="frame", choices=["frame", "fit", "train"],
                     help="frame: BASELINE metric (800x800 FULL render); fit: run_fit.py iteration (1024 rays, fwd+bwd+Adam)")
     return ap.parse_args()
 
@@ -223,7 +223,7 @@ def workload_config(args):
             "l2": "working set (activation buffers, >1 GB per pass) >> 126 MB L2; 256 MB scratch write between timed steps"}
 
 
-def run_fit_workload(args):
+def run_fit_workload(args, train=False):
     """BASELINE config #3: one run_fit.py fitting iteration = 1024 random rays, FULL pipeline, forward + backward to the
     latent codes and the pose, L1 loss, three Adam steps (run_fit.py:281-313).  Not the headline metric: printed as its own
     JSON line for the record."""
@@ -232,6 +232,8 @@ def run_fit_workload(args):
     __graft_entry__.build()
     from mofanerf_b200 import B200Renderer, nets
     coarse, fine, style = nets.build_nets(0, device=dev)
+    coarse.train(train)
+    fine.train(train)
     shape, tex, exp, ro, rd = synth_inputs(256, 256)
     r = B200Renderer(expCodesLen=30).to(dev)
     r.idSpecificMod.load_state_dict(style.state_dict())
@@ -246,15 +248,26 @@ def run_fit_workload(args):
     light = torch.ones(1, device=dev, requires_grad=True)
     opts = [torch.optim.Adam([light, pose_delta], lr=2e-3), torch.optim.Adam([tex], lr=2e-3),
             torch.optim.Adam([exp, shape], lr=4e-3)]
+    if train:   # run_train.py: one Adam over the NeRF weights (+ renderer parameters)
+        opts = [torch.optim.Adam(list(coarse.parameters()) + list(fine.parameters()) + r.grad_parameter(), lr=5e-5)]
     target = torch.rand(n, 3, device=dev)
     ro_d, rd_d = ro.to(dev), rd.to(dev)
     l1 = torch.nn.L1Loss()
 
     def step():
         idx = torch.randint(0, ro_d.shape[0], (n,), generator=g).to(dev)
-        rgb = r.render_fitting(1, n, None, rays=(ro_d[idx] + pose_delta, rd_d[idx]), shapeCodes=shape, uvCodes=tex,
-                               expType=20, expCodes=exp, **kw)[0]
-        loss = l1(rgb * light, target)
+        if train:
+            r.shapeCodes, r.expType, r.decoding_texCodes = shape, 4, tex
+            from mofanerf_b200.rays import pack_rays
+            d = rd_d[idx]
+            r.rays = pack_rays(ro_d[idx], d, 8.0, 26.0, d / torch.norm(d, dim=-1, keepdim=True))
+            ret = r.batchify_rays(1 << 30, network_fn=coarse, network_fine=fine, N_samples=args.n_samples,
+                                  N_importance=args.n_importance, perturb=1.0, raw_noise_std=0.0)
+            loss = torch.mean((ret["rgb_map"] - target) ** 2) + torch.mean((ret["rgb0"] - target) ** 2)
+        else:
+            rgb = r.render_fitting(1, n, None, rays=(ro_d[idx] + pose_delta, rd_d[idx]), shapeCodes=shape, uvCodes=tex,
+                                   expType=20, expCodes=exp, **kw)[0]
+            loss = l1(rgb * light, target)
         for o in opts:
             o.zero_grad()
         loss.backward()
@@ -274,16 +287,20 @@ def run_fit_workload(args):
     ms = e0.elapsed_time(e1) / iters
     fwd = n * (args.n_samples * FLOP_COARSE_PT + (args.n_samples + args.n_importance) * FLOP_FINE_PT)
     bwd = n * (args.n_samples + args.n_importance) * FLOP_FINE_PT       # dX only, fine pass only (rgb0 is not in the loss)
-    print(json.dumps({"metric": "fit iterations/s (run_fit.py: 1024 rays, 64+128 samples, fwd+bwd+Adam)", "value": 1e3 / ms,
+    name = "train iterations/s (run_train.py: 1024 rays, 64+128 samples, fwd+bwd incl. weight gradients+Adam)" if train else \
+        "fit iterations/s (run_fit.py: 1024 rays, 64+128 samples, fwd+bwd+Adam)"
+    if train:   # dX + dW for both passes (rgb0 is in the loss)
+        bwd = 2 * fwd
+    print(json.dumps({"metric": name, "value": 1e3 / ms,
                       "unit": "it/s", "ms_per_iter": ms, "rays_per_s": n * 1e3 / ms, "n_gpus": 1,
                       "algorithmic_tflops": (fwd + bwd) / (ms / 1e3) / 1e12, "data": "synthetic",
-                      "config": {"workload": "BASELINE config #3: fitting loop, N_rand=1024, FULL, 1 x B200"}}), flush=True)
+                      "config": {"workload": ("run_train.py step" if train else "BASELINE config #3: fitting loop") + ", N_rand=1024, FULL, 1 x B200"}}), flush=True)
 
 
 def main():
     args = parse()
-    if args.workload == "fit" and args.impl == "b200":
-        run_fit_workload(args)
+    if args.workload in ("fit", "train") and args.impl == "b200":
+        run_fit_workload(args, train=(args.workload == "train"))
         return
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -64,6 +64,7 @@ struct Layer {
   int seg_c0[2] = {0, 0};        // first column / real width of each activation segment in the reference weight
   int seg_kreal[2] = {0, 0};
   int fold_c0 = 0;               // first latent column
+  int in_total = 0;              // row pitch of the reference weight
   __half* wt[2] = {nullptr, nullptr};
   int rows_t[2] = {0, 0};
   int BN_t[2] = {256, 256};
@@ -163,6 +164,7 @@ int build_layer(mofa_b200_ctx* c, Net& net, const LayerSpec& sp, const float* w,
   L.N = sp.N;
   L.nseg = sp.nseg;
   L.in_ref = sp.in_total;
+  L.in_total = sp.in_total;
   L.BN = (sp.N % 256 == 0) ? 256 : 128;
   if (sp.N % L.BN != 0) return fail("layer width %d is not a multiple of 128", sp.N);
   for (int i = 0; i < sp.nseg; ++i) {
@@ -508,6 +510,31 @@ int mofa_b200_load_weights(mofa_b200_ctx* c, int net_id, int W, int D, const flo
   CK(cudaSetDevice(c->device));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   Net& net = c->nets[net_id];
+  if (net.loaded && net.W == W && net.D == D) {
+    // Same architecture (a training step changed the values): repack into the existing buffers — no allocation, tensor
+    // maps and the fused-kernel tables stay valid.
+    const int nd = static_cast<int>(net.layers.size());
+    for (int li = 0; li < nd; ++li) {
+      Layer& L = net.layers[li];
+      const float* w = t[2 * li];
+      const float* b = t[2 * li + 1];
+      for (int i = 0; i < L.nseg; ++i) {
+        CK(launch_pack_weight(w, L.in_total, L.seg_c0[i], L.seg_kreal[i], L.K[i], L.N, L.w[i], s));
+        CK(launch_pack_weight_t(w, L.in_total, L.seg_c0[i], L.seg_kreal[i], L.rows_t[i], L.N, L.wt[i], s));
+        c->launches += 2;
+      }
+      CK(cudaMemcpyAsync(L.bias_raw, b, sizeof(float) * L.N, cudaMemcpyDeviceToDevice, s));
+      if (L.fold_n > 0)
+        CK(cudaMemcpy2DAsync(L.fold_w, sizeof(float) * L.fold_n, w + L.fold_c0, sizeof(float) * L.in_total,
+                             sizeof(float) * L.fold_n, L.N, cudaMemcpyDeviceToDevice, s));
+    }
+    CK(cudaMemcpyAsync(net.w_alpha, t[2 * nd], sizeof(float) * W, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(net.b_alpha, t[2 * nd + 1], sizeof(float), cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(net.w_rgb, t[2 * nd + 2], sizeof(float) * 3 * (W / 2), cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(net.b_rgb, t[2 * nd + 3], sizeof(float) * 3, cudaMemcpyDeviceToDevice, s));
+    if (c->latents_set && fold_net(c, net, s)) return 1;
+    return 0;
+  }
   free_net(net);
   net.W = W;
   net.D = D;
