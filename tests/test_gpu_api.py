@@ -158,3 +158,52 @@ def test_config2_400x400_full_frame_properties():
         ref_rays = O.make_ray_batch(ro.reshape(-1, 3)[idx[:12]].cpu(), rd.reshape(-1, 3)[idx[:12]].cpu(), 8.0, 26.0)
         ref = O.render_rays(ref_rays, c.cpu(), f.cpu(), inp["shape"], O.expression_mod(s, inp["shape"], inp["exp"]), inp["tex"])
         assert (sub[:12].cpu() - ref["rgb_map"]).abs().max().item() <= 6e-2
+
+
+@pytest.mark.parametrize("n,S,Ni,wb,lindisp", [(1, 64, 64, False, False), (3, 32, 64, True, False), (130, 16, 16, False, True),
+                                               (5, 128, 128, False, False), (2, 2, 0, False, False), (7, 256, 0, True, False)])
+def test_edge_sizes_match_oracle(n, S, Ni, wb, lindisp):
+    """Ragged / extreme sizes: single ray, point counts that are not multiples of the 128-row tile, S_f = 96 / 256, the
+    smallest and largest sample counts, coarse-only passes, white background and inverse-depth sampling.  Coarse maps are
+    compared tightly (no resampling feedback); final maps at the end-to-end bound."""
+    meta, inp, _ = load_case("small_w256")
+    c, f, s = build_case_nets(meta)
+    ro, rd = inp["rays_o"][:n], inp["rays_d"][:n]
+    rays = O.make_ray_batch(ro, rd, 8.0, 26.0)
+    with torch.no_grad():
+        ref = O.render_rays(rays, c, f, inp["shape"], O.expression_mod(s, inp["shape"], inp["exp"]), inp["tex"],
+                            N_samples=S, N_importance=Ni, white_bkgd=wb, lindisp=lindisp)
+    r = _renderer(s)
+    with torch.no_grad():
+        rgb, disp, acc, ex = r.render_fitting(1, n, None, rays=(ro.to(DEV), rd.to(DEV)), shapeCodes=inp["shape"].to(DEV),
+                                              uvCodes=inp["tex"].to(DEV), expType=20, expCodes=inp["exp"].to(DEV),
+                                              **_kw(c, f, N_samples=S, N_importance=Ni, white_bkgd=wb, lindisp=lindisp))
+    assert rgb.shape == (1, n, 3) or rgb.shape == (n, 3)
+    rgb = rgb.reshape(n, 3).cpu()
+    if Ni > 0:
+        d0 = (ex["rgb0"].reshape(n, 3).cpu() - ref["rgb0"]).abs().max().item()
+        assert d0 <= 4e-3, f"rgb0 {d0:.2e}"
+        assert (rgb - ref["rgb_map"]).abs().max().item() <= 6e-2
+    else:
+        assert "rgb0" not in ex
+        assert (rgb - ref["rgb_map"]).abs().max().item() <= 4e-3
+        assert (acc.reshape(n).cpu() - ref["acc_map"]).abs().max().item() <= 4e-3
+
+
+def test_invalid_arguments_fail_loudly():
+    from mofanerf_b200 import get_engine
+    eng = get_engine(DEV)
+    meta, inp, _ = load_case("small_w256")
+    c, f, s = build_case_nets(meta)
+    eng.load_network(0, c.to(DEV), force=True)
+    eng.load_network(1, f.to(DEV), force=True)
+    eng.set_latents(inp["shape"], inp["exp"] * 0, inp["tex"])
+    rays = torch.zeros(4, 11, device=DEV)
+    with pytest.raises(RuntimeError, match="n_samples"):
+        eng.render_rays(rays, 1, 0)                       # the reference degenerates at one sample; refused
+    with pytest.raises(RuntimeError, match="out of range"):
+        eng.render_rays(rays, 200, 100)                   # S_c + N_i > 256
+    with pytest.raises(ValueError):
+        eng.set_latents(torch.zeros(49), torch.zeros(30), torch.zeros(256))
+    with pytest.raises(ValueError, match="engine on"):
+        eng.render_rays(torch.zeros(4, 11), 8, 0)         # host tensor handed to the device entry point
