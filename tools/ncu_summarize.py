@@ -69,7 +69,7 @@ def full(src, dst, json_out=None):
              "dram_bytes_per_launch": tobytes("dram__bytes_read.sum") + tobytes("dram__bytes_write.sum"),
              "tensor_pipe_active_pct_elapsed": float(out["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed"]["values"][-1]),
              "duration_us": float(out["gpu__time_duration.sum"]["values"][-1]),
-             "launch": "fine-net layer: M=262144 (2048 rays x 128 samples), N=1024, K=1024"}
+             "launch": "fine-net 1024->1024 layer at bench.py --H 256 --W 256: M = 530432 rows (one default chunk of 4144 rays x 128 samples), N=1024, K=1024"}
         json.dump(j, open(json_out, "w"), indent=1)
 
 
