@@ -32,7 +32,7 @@ struct EpiParams {
 template <int BN, bool BWD>
 __device__ __forceinline__ void epilogue_tile(const EpiParams& p, const void* tmC, uint32_t acc_addr, uint32_t cbuf0,
                                               uint32_t& cnt, int m0, int n0, int n_tile, int row, int ep_tid) {
-  float hacc[3] = {0.f, 0.f, 0.f};
+  float hacc[3][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
   const float r1 = (BWD && p.r1_row != nullptr && m0 + row < p.M) ? p.r1_row[static_cast<size_t>(m0 + row) * p.r1_stride] : 0.0f;
 #pragma unroll 1
   for (int cb = 0; cb < BN / 64; ++cb) {
@@ -74,14 +74,21 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& p, const void* tm
           if (BWD && !(__half2float(mh[e]) > 0.0f)) x = 0.0f;
           f[e] = fminf(fmaxf(x, -65504.0f), 65504.0f);
         }
-        if (p.head_n > 0) {
+        // fused head: four independent partial sums per output (one per 8-column group j) keep the FMA chains short —
+        // a single running sum made the sigma / view layers 45 % slower than a plain layer (dependent-FMA latency in an
+        // epilogue that has little slack against the tile's MMA time)
+        if (p.head_n == 1) {
+          const float4* w4 = reinterpret_cast<const float4*>(p.head_w + ncol) + 2 * j;
+          const float4 w0 = __ldg(w4), w1 = __ldg(w4 + 1);
+          hacc[0][j] += (f[0] * w0.x + f[1] * w0.y) + (f[2] * w0.z + f[3] * w0.w) + (f[4] * w1.x + f[5] * w1.y) +
+                        (f[6] * w1.z + f[7] * w1.w);
+        } else if (p.head_n == 3) {
 #pragma unroll
           for (int q = 0; q < 3; ++q) {
-            if (q >= p.head_n) break;
             const float4* w4 = reinterpret_cast<const float4*>(p.head_w + static_cast<size_t>(q) * p.N + ncol) + 2 * j;
             const float4 w0 = __ldg(w4), w1 = __ldg(w4 + 1);
-            hacc[q] += f[0] * w0.x + f[1] * w0.y + f[2] * w0.z + f[3] * w0.w + f[4] * w1.x + f[5] * w1.y +
-                       f[6] * w1.z + f[7] * w1.w;
+            hacc[q][j] += (f[0] * w0.x + f[1] * w0.y) + (f[2] * w0.z + f[3] * w0.w) + (f[4] * w1.x + f[5] * w1.y) +
+                          (f[6] * w1.z + f[7] * w1.w);
           }
         }
         if (p.store_c) {
@@ -112,7 +119,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& p, const void* tm
     float* dst = p.head_out + static_cast<size_t>(m0 + row) * p.head_stride + p.head_slot0 + n_tile * p.head_n;
 #pragma unroll
     for (int q = 0; q < 3; ++q)
-      if (q < p.head_n) dst[q] = hacc[q];
+      if (q < p.head_n) dst[q] = (hacc[q][0] + hacc[q][1]) + (hacc[q][2] + hacc[q][3]);
   }
 }
 
