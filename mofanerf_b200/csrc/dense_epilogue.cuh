@@ -32,7 +32,7 @@ struct EpiParams {
 template <int BN, bool BWD>
 __device__ __forceinline__ void epilogue_tile(const EpiParams& p, const void* tmC, uint32_t acc_addr, uint32_t cbuf0,
                                               uint32_t& cnt, int m0, int n0, int n_tile, int row, int ep_tid) {
-  float hacc[3][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  float hacc[3] = {0.f, 0.f, 0.f};
   const float r1 = (BWD && p.r1_row != nullptr && m0 + row < p.M) ? p.r1_row[static_cast<size_t>(m0 + row) * p.r1_stride] : 0.0f;
 #pragma unroll 1
   for (int cb = 0; cb < BN / 64; ++cb) {
@@ -41,15 +41,11 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& p, const void* tm
       if (ep_tid == 0) tma_store_wait_read<1>();    // the store that last read this buffer is done
       named_bar_sync(1, 128);
     }
-    // both 32-column halves of the block are requested before the single wait: one exposed TMEM latency per 64 columns
-    // (nothing sits between the loads and the wait, so the destination registers are not touched while in flight)
-    uint32_t vv[2][32];
-    tmem_ld_32x32b_x32(acc_addr + cb * 64, vv[0]);
-    tmem_ld_32x32b_x32(acc_addr + cb * 64 + 32, vv[1]);
-    tmem_ld_wait();
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      uint32_t (&v)[32] = vv[h];
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(acc_addr + cb * 64 + h * 32, v);
+      tmem_ld_wait();
       const int ncol = n0 + cb * 64 + h * 32;
       const float4* bias4 = reinterpret_cast<const float4*>(p.bias + ncol);   // 128-byte aligned (ncol % 32 == 0)
 #pragma unroll
@@ -71,52 +67,33 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& p, const void* tm
         if (BWD && p.mask != nullptr && m0 + row < p.M)
           mk = __ldg(reinterpret_cast<const uint4*>(p.mask + static_cast<size_t>(m0 + row) * p.N + ncol) + j);
         const __half* mh = reinterpret_cast<const __half*>(&mk);
-        float g[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          g[e] = __uint_as_float(v[j * 8 + e]) + bb[e];
-          float x = g[e];
+          float x = __uint_as_float(v[j * 8 + e]) + bb[e];
           if (p.relu) x = fmaxf(x, 0.0f);
           if (BWD && !(__half2float(mh[e]) > 0.0f)) x = 0.0f;
-          f[e] = (BWD || !p.relu) ? fminf(fmaxf(x, -65504.0f), 65504.0f) : x;   // forward+ReLU: saturation happens in the packed min
+          f[e] = fminf(fmaxf(x, -65504.0f), 65504.0f);
         }
-        // fused head: four independent partial sums per output (one per 8-column group j) keep the FMA chains short —
-        // a single running sum made the sigma / view layers 45 % slower than a plain layer (dependent-FMA latency in an
-        // epilogue that has little slack against the tile's MMA time)
-        if (p.head_n == 1) {
-          const float4* w4 = reinterpret_cast<const float4*>(p.head_w + ncol) + 2 * j;
-          const float4 w0 = __ldg(w4), w1 = __ldg(w4 + 1);
-          hacc[0][j] += (f[0] * w0.x + f[1] * w0.y) + (f[2] * w0.z + f[3] * w0.w) + (f[4] * w1.x + f[5] * w1.y) +
-                        (f[6] * w1.z + f[7] * w1.w);
-        } else if (p.head_n == 3) {
+        if (p.head_n > 0) {
 #pragma unroll
           for (int q = 0; q < 3; ++q) {
+            if (q >= p.head_n) break;
             const float4* w4 = reinterpret_cast<const float4*>(p.head_w + static_cast<size_t>(q) * p.N + ncol) + 2 * j;
             const float4 w0 = __ldg(w4), w1 = __ldg(w4 + 1);
-            hacc[q][j] += (f[0] * w0.x + f[1] * w0.y) + (f[2] * w0.z + f[3] * w0.w) + (f[4] * w1.x + f[5] * w1.y) +
-                          (f[6] * w1.z + f[7] * w1.w);
+            hacc[q] += f[0] * w0.x + f[1] * w0.y + f[2] * w0.z + f[3] * w0.w + f[4] * w1.x + f[5] * w1.y +
+                       f[6] * w1.z + f[7] * w1.w;
           }
         }
         if (p.store_c) {
-          uint32_t pk[4];
-          if (!BWD && p.relu) {
-            // x was already clamped to [0, 65504] above for the head; for the stored copy use the single-instruction
-            // ReLU + convert (cvt.rn.relu.f16x2.f32) on the UNclamped sum and a packed min against the fp16 maximum
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(pk[e]) : "f"(g[2 * e + 1]), "f"(g[2 * e]));
-              asm("min.f16x2 %0, %0, %1;" : "+r"(pk[e]) : "r"(0x7bff7bffu));
-            }
-          } else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              __half2 hh = __floats2half2_rn(f[2 * e], f[2 * e + 1]);
-              pk[e] = *reinterpret_cast<uint32_t*>(&hh);
-            }
-          }
+          __half2 h0 = __floats2half2_rn(f[0], f[1]);
+          __half2 h1 = __floats2half2_rn(f[2], f[3]);
+          __half2 h2 = __floats2half2_rn(f[4], f[5]);
+          __half2 h3 = __floats2half2_rn(f[6], f[7]);
           const int chunk = h * 4 + j;              // 16-byte chunk within the 128-byte row
           const uint32_t addr = cbuf + row * 128 + ((chunk ^ (row & 7)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3])
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
+                       "r"(*reinterpret_cast<uint32_t*>(&h0)), "r"(*reinterpret_cast<uint32_t*>(&h1)),
+                       "r"(*reinterpret_cast<uint32_t*>(&h2)), "r"(*reinterpret_cast<uint32_t*>(&h3))
                        : "memory");
         }
       }
@@ -135,7 +112,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& p, const void* tm
     float* dst = p.head_out + static_cast<size_t>(m0 + row) * p.head_stride + p.head_slot0 + n_tile * p.head_n;
 #pragma unroll
     for (int q = 0; q < 3; ++q)
-      if (q < p.head_n) dst[q] = (hacc[q][0] + hacc[q][1]) + (hacc[q][2] + hacc[q][3]);
+      if (q < p.head_n) dst[q] = hacc[q];
   }
 }
 
