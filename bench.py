@@ -49,6 +49,9 @@ def parse():
     ap.add_argument("--chunk-rays", type=int, default=0, help="engine-internal rays per pass (0 = default)")
     ap.add_argument("--cpu-sample-rays", type=int, default=0, help="rays in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--torch-gpu-baseline", action="store_true",
+                    help="also time the reference algorithm (fp32 PyTorch port) on this GPU, the denominator of the "
+                         "north_star's '>=10x the reference single-GPU PyTorch path'; opt-in, adds 'torch_gpu_baseline'")
     ap.add_argument("--workload", default="frame", choices=["frame", "fit", "train"],
                     help="frame: BASELINE metric (800x800 FULL render); fit: run_fit.py iteration (1024 rays, fwd+bwd+Adam)")
     return ap.parse_args()
@@ -175,6 +178,33 @@ def cpu_baseline(n_s, n_i, sample_rays, max_seconds=25.0):
     return {"value": n / dt, "unit": "rays/s", "cores": cores, "kind": "port",
             "sample": f"{n} rays x ({n_s} coarse + {n_s + n_i} fine) samples, fp32, oracle/mofa_oracle.py, {dt:.1f} s, "
                       f"{cores} torch threads (fastest of all/half/quarter/eighth of {logical} logical CPUs)"}
+
+
+def torch_gpu_baseline(n_s, n_i, dev, n_rays=8192):
+    """The reference algorithm as PyTorch eager kernels on the same B200 (fp32 cuBLAS, then with TF32 allowed):
+    context for the speed-up, not a target.  Uses the oracle port because /root/reference is absent on the GPU box."""
+    from oracle import mofa_oracle as O
+    c, f, s = O.build_nets(0)
+    c, f, s = c.to(dev), f.to(dev), s.to(dev)
+    shape, tex, exp, ro, rd = synth_inputs(128, 128)
+    idx = torch.linspace(0, ro.shape[0] - 1, n_rays).long()
+    out = {"sample": f"{n_rays} rays x ({n_s} coarse + {n_s + n_i} fine) samples, oracle port on cuda, netchunk 65536"}
+    with torch.no_grad(), torch.device(dev):
+        rays = O.make_ray_batch(ro[idx].to(dev), rd[idx].to(dev), 8.0, 26.0)
+        shape, tex, exp = shape.to(dev), tex.to(dev), exp.to(dev)
+        em = O.expression_mod(s, shape, exp)
+        for name, tf32 in (("fp32", False), ("tf32", True)):
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            for _ in range(2):
+                O.render_rays(rays, c, f, shape, em, tex, N_samples=n_s, N_importance=n_i)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                O.render_rays(rays, c, f, shape, em, tex, N_samples=n_s, N_importance=n_i)
+            torch.cuda.synchronize()
+            out[f"rays_per_s_{name}"] = 3 * n_rays / (time.perf_counter() - t0)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return out
 
 
 def run_reference(args, rank, world):
@@ -442,6 +472,8 @@ def main():
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args.n_samples, args.n_importance, args.cpu_sample_rays)
+    if world == 1 and args.torch_gpu_baseline:
+        line["torch_gpu_baseline"] = torch_gpu_baseline(args.n_samples, args.n_importance, dev)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
