@@ -29,8 +29,11 @@ struct EpiParams {
 
 // acc_addr: TMEM address of this warp's lane quadrant at the accumulator stage's first column.
 // cbuf0: shared address of the two 16 KB staging buffers.  cnt: running staging-buffer counter.
-template <int BN, bool BWD>
-__device__ __forceinline__ void epilogue_tile(const EpiParams& p, const void* tmC, uint32_t acc_addr, uint32_t cbuf0,
+// HEAD = number of fused head outputs (0, 1, 3), a compile-time copy of p.head_n: the head weights of a 32-column
+// chunk are fetched while the chunk's TMEM load is in flight.  (Fetched where they are used — inside a branch on
+// p.head_n — every 8-column group exposed a full L1/L2 latency: ncu source page, 30 % of the sigma layer's time.)
+template <int BN, bool BWD, int HEAD>
+__device__ __forceinline__ void epilogue_tile_impl(const EpiParams& p, const void* tmC, uint32_t acc_addr, uint32_t cbuf0,
                                               uint32_t& cnt, int m0, int n0, int n_tile, int row, int ep_tid) {
   float hacc[3] = {0.f, 0.f, 0.f};
   const float r1 = (BWD && p.r1_row != nullptr && m0 + row < p.M) ? p.r1_row[static_cast<size_t>(m0 + row) * p.r1_stride] : 0.0f;
@@ -45,8 +48,17 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& p, const void* tm
     for (int h = 0; h < 2; ++h) {
       uint32_t v[32];
       tmem_ld_32x32b_x32(acc_addr + cb * 64 + h * 32, v);
-      tmem_ld_wait();
       const int ncol = n0 + cb * 64 + h * 32;
+      float4 hw[HEAD > 0 ? HEAD * 8 : 1];
+      if constexpr (HEAD > 0) {
+#pragma unroll
+        for (int q = 0; q < HEAD; ++q) {
+          const float4* w4 = reinterpret_cast<const float4*>(p.head_w + static_cast<size_t>(q) * p.N + ncol);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) hw[q * 8 + i] = __ldg(w4 + i);
+        }
+      }
+      tmem_ld_wait();
       const float4* bias4 = reinterpret_cast<const float4*>(p.bias + ncol);   // 128-byte aligned (ncol % 32 == 0)
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -74,12 +86,10 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& p, const void* tm
           if (BWD && !(__half2float(mh[e]) > 0.0f)) x = 0.0f;
           f[e] = fminf(fmaxf(x, -65504.0f), 65504.0f);
         }
-        if (p.head_n > 0) {
+        if constexpr (HEAD > 0) {
 #pragma unroll
-          for (int q = 0; q < 3; ++q) {
-            if (q >= p.head_n) break;
-            const float4* w4 = reinterpret_cast<const float4*>(p.head_w + static_cast<size_t>(q) * p.N + ncol) + 2 * j;
-            const float4 w0 = __ldg(w4), w1 = __ldg(w4 + 1);
+          for (int q = 0; q < HEAD; ++q) {
+            const float4 w0 = hw[q * 8 + 2 * j], w1 = hw[q * 8 + 2 * j + 1];
             hacc[q] += f[0] * w0.x + f[1] * w0.y + f[2] * w0.z + f[3] * w0.w + f[4] * w1.x + f[5] * w1.y +
                        f[6] * w1.z + f[7] * w1.w;
           }
@@ -108,11 +118,24 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& p, const void* tm
       ++cnt;
     }
   }
-  if (p.head_n > 0 && m0 + row < p.M) {
-    float* dst = p.head_out + static_cast<size_t>(m0 + row) * p.head_stride + p.head_slot0 + n_tile * p.head_n;
+  if constexpr (HEAD > 0) {
+    if (m0 + row < p.M) {
+      float* dst = p.head_out + static_cast<size_t>(m0 + row) * p.head_stride + p.head_slot0 + n_tile * HEAD;
 #pragma unroll
-    for (int q = 0; q < 3; ++q)
-      if (q < p.head_n) dst[q] = hacc[q];
+      for (int q = 0; q < HEAD; ++q) dst[q] = hacc[q];
+    }
+  }
+}
+
+template <int BN, bool BWD>
+__device__ __forceinline__ void epilogue_tile(const EpiParams& p, const void* tmC, uint32_t acc_addr, uint32_t cbuf0,
+                                              uint32_t& cnt, int m0, int n0, int n_tile, int row, int ep_tid) {
+  if constexpr (BWD) {
+    epilogue_tile_impl<BN, BWD, 0>(p, tmC, acc_addr, cbuf0, cnt, m0, n0, n_tile, row, ep_tid);
+  } else {
+    if (p.head_n == 0) epilogue_tile_impl<BN, BWD, 0>(p, tmC, acc_addr, cbuf0, cnt, m0, n0, n_tile, row, ep_tid);
+    else if (p.head_n == 1) epilogue_tile_impl<BN, BWD, 1>(p, tmC, acc_addr, cbuf0, cnt, m0, n0, n_tile, row, ep_tid);
+    else epilogue_tile_impl<BN, BWD, 3>(p, tmC, acc_addr, cbuf0, cnt, m0, n0, n_tile, row, ep_tid);
   }
 }
 
