@@ -27,35 +27,58 @@ struct EpiParams {
   int r1_stride;
 };
 
+// Read-only 16-byte load that the compiler may not move across the other volatile asm statements of the epilogue
+// (TMEM load / wait, staging stores): pins WHERE a prefetch is issued, which __ldg does not.
+__device__ __forceinline__ float4 ldg_f4_pinned(const float4* ptr) {
+  float4 r;
+  asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(ptr));
+  return r;
+}
+
+// One epilogue GROUP = 4 warps (one per TMEM lane quadrant) that own a range of 64-column blocks of the tile, their
+// own staging buffer(s), their own named barrier and their own head slot.  The single-CTA kernel and the 4-warp pair
+// kernel run one group over all BN columns; the 8-warp pair kernel runs two groups on one half of the columns each.
+struct EpiGroup {
+  uint32_t cbuf0;   // shared address of this group's staging buffer(s), 16 KB each
+  int cb0, cb1;     // 64-column blocks [cb0, cb1) of the tile
+  int bar_id;       // named barrier shared by the group's 128 threads
+  int slot;         // head partial slot of this (n-tile, group)
+  int gtid;         // thread index within the group, 0..127
+};
+
 // acc_addr: TMEM address of this warp's lane quadrant at the accumulator stage's first column.
-// cbuf0: shared address of the two 16 KB staging buffers.  cnt: running staging-buffer counter.
+// cnt: running staging-buffer counter (NBUF == 2).  NBUF: staging buffers the group alternates between.
 // HEAD = number of fused head outputs (0, 1, 3), a compile-time copy of p.head_n: the head weights of a 32-column
 // chunk are fetched while the chunk's TMEM load is in flight.  (Fetched where they are used — inside a branch on
 // p.head_n — every 8-column group exposed a full L1/L2 latency: ncu source page, 30 % of the sigma layer's time.)
-template <int BN, bool BWD, int HEAD>
-__device__ __forceinline__ void epilogue_tile_impl(const EpiParams& p, const void* tmC, uint32_t acc_addr, uint32_t cbuf0,
-                                              uint32_t& cnt, int m0, int n0, int n_tile, int row, int ep_tid) {
+template <int BN, bool BWD, int HEAD, int NBUF>
+__device__ __forceinline__ void epilogue_tile_impl(const EpiParams& p, const void* tmC, uint32_t acc_addr,
+                                                   const EpiGroup& g, uint32_t& cnt, int m0, int n0, int row) {
   float hacc[3] = {0.f, 0.f, 0.f};
   const float r1 = (BWD && p.r1_row != nullptr && m0 + row < p.M) ? p.r1_row[static_cast<size_t>(m0 + row) * p.r1_stride] : 0.0f;
 #pragma unroll 1
-  for (int cb = 0; cb < BN / 64; ++cb) {
-    const uint32_t cbuf = cbuf0 + (cnt & 1u) * (128 * 64 * 2);
+  for (int cb = g.cb0; cb < g.cb1; ++cb) {
+    const uint32_t cbuf = g.cbuf0 + (NBUF == 2 ? (cnt & 1u) * (128 * 64 * 2) : 0u);
     if (p.store_c) {
-      if (ep_tid == 0) tma_store_wait_read<1>();    // the store that last read this buffer is done
-      named_bar_sync(1, 128);
+      if (g.gtid == 0) tma_store_wait_read<NBUF - 1>();    // the store that last read this buffer is done
+      named_bar_sync(g.bar_id, 128);
     }
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       uint32_t v[32];
       tmem_ld_32x32b_x32(acc_addr + cb * 64 + h * 32, v);
       const int ncol = n0 + cb * 64 + h * 32;
-      float4 hw[HEAD > 0 ? HEAD * 8 : 1];
+      // head weights: HEAD == 1 fetches the whole 32-column chunk here (32 registers); HEAD == 3 would need 96, so it
+      // fetches one 8-column block ahead of the block being reduced (two rotating sets of 24 registers)
+      constexpr int HB = (HEAD == 3) ? 1 : 4;           // 8-column blocks per fetch
+      constexpr int NHW = HEAD > 0 ? HEAD * 2 * HB : 1;
+      float4 hw[2][NHW];
       if constexpr (HEAD > 0) {
 #pragma unroll
         for (int q = 0; q < HEAD; ++q) {
           const float4* w4 = reinterpret_cast<const float4*>(p.head_w + static_cast<size_t>(q) * p.N + ncol);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) hw[q * 8 + i] = __ldg(w4 + i);
+          for (int i = 0; i < 2 * HB; ++i) hw[0][q * 2 * HB + i] = ldg_f4_pinned(w4 + i);
         }
       }
       tmem_ld_wait();
@@ -86,10 +109,21 @@ __device__ __forceinline__ void epilogue_tile_impl(const EpiParams& p, const voi
           if (BWD && !(__half2float(mh[e]) > 0.0f)) x = 0.0f;
           f[e] = fminf(fmaxf(x, -65504.0f), 65504.0f);
         }
+        if constexpr (HEAD > 0 && HB == 1) {
+          if (j + 1 < 4) {
+#pragma unroll
+            for (int q = 0; q < HEAD; ++q) {
+              const float4* w4 = reinterpret_cast<const float4*>(p.head_w + static_cast<size_t>(q) * p.N + ncol) + 2 * (j + 1);
+              hw[(j + 1) & 1][q * 2] = ldg_f4_pinned(w4);
+              hw[(j + 1) & 1][q * 2 + 1] = ldg_f4_pinned(w4 + 1);
+            }
+          }
+        }
         if constexpr (HEAD > 0) {
 #pragma unroll
           for (int q = 0; q < HEAD; ++q) {
-            const float4 w0 = hw[q * 8 + 2 * j], w1 = hw[q * 8 + 2 * j + 1];
+            const float4 w0 = HB == 1 ? hw[j & 1][q * 2] : hw[0][q * 2 * HB + 2 * j];
+            const float4 w1 = HB == 1 ? hw[j & 1][q * 2 + 1] : hw[0][q * 2 * HB + 2 * j + 1];
             hacc[q] += f[0] * w0.x + f[1] * w0.y + f[2] * w0.z + f[3] * w0.w + f[4] * w1.x + f[5] * w1.y +
                        f[6] * w1.z + f[7] * w1.w;
           }
@@ -110,8 +144,8 @@ __device__ __forceinline__ void epilogue_tile_impl(const EpiParams& p, const voi
     }
     if (p.store_c) {
       fence_proxy_async_smem();
-      named_bar_sync(1, 128);
-      if (ep_tid == 0) {
+      named_bar_sync(g.bar_id, 128);
+      if (g.gtid == 0) {
         tma_store_2d(tmC, cbuf, n0 + cb * 64, m0);
         tma_store_commit();
       }
@@ -120,22 +154,22 @@ __device__ __forceinline__ void epilogue_tile_impl(const EpiParams& p, const voi
   }
   if constexpr (HEAD > 0) {
     if (m0 + row < p.M) {
-      float* dst = p.head_out + static_cast<size_t>(m0 + row) * p.head_stride + p.head_slot0 + n_tile * HEAD;
+      float* dst = p.head_out + static_cast<size_t>(m0 + row) * p.head_stride + p.head_slot0 + g.slot * HEAD;
 #pragma unroll
       for (int q = 0; q < HEAD; ++q) dst[q] = hacc[q];
     }
   }
 }
 
-template <int BN, bool BWD>
-__device__ __forceinline__ void epilogue_tile(const EpiParams& p, const void* tmC, uint32_t acc_addr, uint32_t cbuf0,
-                                              uint32_t& cnt, int m0, int n0, int n_tile, int row, int ep_tid) {
+template <int BN, bool BWD, int NBUF>
+__device__ __forceinline__ void epilogue_tile(const EpiParams& p, const void* tmC, uint32_t acc_addr, const EpiGroup& g,
+                                              uint32_t& cnt, int m0, int n0, int row) {
   if constexpr (BWD) {
-    epilogue_tile_impl<BN, BWD, 0>(p, tmC, acc_addr, cbuf0, cnt, m0, n0, n_tile, row, ep_tid);
+    epilogue_tile_impl<BN, BWD, 0, NBUF>(p, tmC, acc_addr, g, cnt, m0, n0, row);
   } else {
-    if (p.head_n == 0) epilogue_tile_impl<BN, BWD, 0>(p, tmC, acc_addr, cbuf0, cnt, m0, n0, n_tile, row, ep_tid);
-    else if (p.head_n == 1) epilogue_tile_impl<BN, BWD, 1>(p, tmC, acc_addr, cbuf0, cnt, m0, n0, n_tile, row, ep_tid);
-    else epilogue_tile_impl<BN, BWD, 3>(p, tmC, acc_addr, cbuf0, cnt, m0, n0, n_tile, row, ep_tid);
+    if (p.head_n == 0) epilogue_tile_impl<BN, BWD, 0, NBUF>(p, tmC, acc_addr, g, cnt, m0, n0, row);
+    else if (p.head_n == 1) epilogue_tile_impl<BN, BWD, 1, NBUF>(p, tmC, acc_addr, g, cnt, m0, n0, row);
+    else epilogue_tile_impl<BN, BWD, 3, NBUF>(p, tmC, acc_addr, g, cnt, m0, n0, row);
   }
 }
 

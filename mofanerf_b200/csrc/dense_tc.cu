@@ -170,8 +170,8 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(tfull0 + 8 * as, aphase);
       tc_fence_after();
-      epilogue_tile<BN, BWD>(p.epi, &tmC, tmem_base + lane_base + as * BN, base + L::OFF_C, cnt, m0, n0, t % p.n_tiles, row,
-                        ep_tid);
+      const EpiGroup g{base + L::OFF_C, 0, BN / 64, 1, t % p.n_tiles, ep_tid};
+      epilogue_tile<BN, BWD, 2>(p.epi, &tmC, tmem_base + lane_base + as * BN, g, cnt, m0, n0, row);
       tc_fence_before();
       mbar_arrive(tempty0 + 8 * as);                // 128 arrivals release the accumulator stage
     }

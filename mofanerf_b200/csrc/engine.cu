@@ -36,7 +36,8 @@ constexpr int kNShape = 50, kNExp = 30, kNTex = 256, kMultires = 10, kMultiresVi
 constexpr int kPeXyz = 3 + 6 * kMultires;        // 63
 constexpr int kPeView = 3 + 6 * kMultiresViews;  // 27
 constexpr int kMaxSms = 160;
-constexpr int kHeadStride = 16;                  // fp32 partial-head slots per point: alpha tiles at 0..3, rgb at 4..15
+constexpr int kHeadStride = 32;                  // fp32 partial-head slots per point: alpha at 0..7, rgb (x3) at 8..31
+constexpr int kRgbSlot0 = 8;
 
 using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -331,6 +332,10 @@ int run_program(mofa_b200_ctx* c, Net& net, const Workspace& ws, int64_t P_rows,
   const int r_bn = ((net.W / 2) % 256 == 0) ? 256 : 128;
   const int r_tiles = (net.W / 2) / r_bn;
   const bool fuse_heads = tc && a_tiles <= 4 && r_tiles <= 4;
+  // a layer run by the pair kernel writes one partial slot per (n-tile, epilogue group)
+  const int pair_groups = c->pair_kernel ? dense_tc2_head_groups() : 1;
+  const int a_slots = a_tiles * ((net.W >= 512) ? pair_groups : 1);
+  const int r_slots = r_tiles * ((r_bn == 256 && net.W / 2 >= 512) ? pair_groups : 1);
   for (const Step& st : net.program) {
     if (st.kind == 0) {
       const Layer& L = net.layers[st.layer];
@@ -355,7 +360,7 @@ int run_program(mofa_b200_ctx* c, Net& net, const Workspace& ws, int64_t P_rows,
       if (fuse_heads && st.head == 1) {
         d.head_w = net.w_alpha; d.head_out = ws.hp; d.head_n = 1; d.head_stride = kHeadStride; d.head_slot0 = 0;
       } else if (fuse_heads && st.head == 2) {
-        d.head_w = net.w_rgb; d.head_out = ws.hp; d.head_n = 3; d.head_stride = kHeadStride; d.head_slot0 = 4;
+        d.head_w = net.w_rgb; d.head_out = ws.hp; d.head_n = 3; d.head_stride = kHeadStride; d.head_slot0 = kRgbSlot0;
         d.store_c = act ? 1 : 0;   // the backward pass needs the view layer's activation (ReLU')
       }
       if (!tc) {
@@ -397,7 +402,7 @@ int run_program(mofa_b200_ctx* c, Net& net, const Workspace& ws, int64_t P_rows,
     }
   }
   if (fuse_heads) {
-    CK(launch_finalize_raw(ws.hp, kHeadStride, 0, a_tiles, 4, r_tiles, net.b_alpha, net.b_rgb, ws.raw, P_rows, s));
+    CK(launch_finalize_raw(ws.hp, kHeadStride, 0, a_slots, kRgbSlot0, r_slots, net.b_alpha, net.b_rgb, ws.raw, P_rows, s));
     c->launches++;
   }
   return 0;

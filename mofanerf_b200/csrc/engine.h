@@ -26,7 +26,7 @@ struct DenseLaunch {
   int BN;               // 128 or 256
   int relu;
   // fused output head (tensor-core kernels only): partial dot products of the activated tile rows with
-  // head_w [head_n, N] go to head_out[row * head_stride + head_slot0 + n_tile * head_n + q]
+  // head_w [head_n, N] go to head_out[row * head_stride + head_slot0 + slot * head_n + q], slot = n_tile (x groups + group)
   const float* head_w;
   float* head_out;
   int head_n, head_stride, head_slot0;
@@ -45,6 +45,8 @@ cudaError_t dense_tc_configure();   // one-time cudaFuncSetAttribute for the ker
 // CTA-pair (cta_group::2) kernel, N % 256 == 0: 256x256 tile per pair of SMs (dense_tc2.cu)
 cudaError_t launch_dense_tc2(const DenseLaunch& L, int num_sms, cudaStream_t stream);
 cudaError_t dense_tc2_configure();
+// head partial slots the pair kernel writes per 256-column tile (1, or 2 with the two-group epilogue)
+int dense_tc2_head_groups();
 
 // ---- element-wise / per-ray kernels (sampling.cu) -----------------------------------------------
 cudaError_t launch_zvals_coarse(const float* rays, int stride, int64_t n, int S, int lindisp, float perturb,
