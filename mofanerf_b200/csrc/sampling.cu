@@ -543,11 +543,46 @@ __global__ void finalize_raw_kernel(const float* __restrict__ hp, int stride, in
   reinterpret_cast<float4*>(raw)[p] = make_float4(r + b_rgb[0], g + b_rgb[1], b + b_rgb[2], a + b_alpha[0]);
 }
 
+// Same reduction with the slot layout known at compile time: the 128-byte slot row is read with 16-byte loads (only the
+// quarters that hold live slots) instead of one scalar load per slot.
+template <int STRIDE, int A0, int R0>
+__global__ void finalize_raw_vec_kernel(const float* __restrict__ hp, int a_tiles, int r_tiles,
+                                        const float* __restrict__ b_alpha, const float* __restrict__ b_rgb,
+                                        float* __restrict__ raw, int64_t P) {
+  const int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const float4* h4 = reinterpret_cast<const float4*>(hp + p * STRIDE);
+  float row[STRIDE];
+#pragma unroll
+  for (int i = 0; i < STRIDE / 4; ++i) {
+    const bool need = (4 * i < A0 + a_tiles && 4 * i + 4 > A0) || (4 * i < R0 + 3 * r_tiles && 4 * i + 4 > R0);
+    const float4 v = need ? __ldg(h4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    row[4 * i] = v.x; row[4 * i + 1] = v.y; row[4 * i + 2] = v.z; row[4 * i + 3] = v.w;
+  }
+  float a = 0.f, r = 0.f, g = 0.f, b = 0.f;
+#pragma unroll
+  for (int t = 0; t < R0 - A0; ++t)
+    if (t < a_tiles) a += row[A0 + t];                              // fixed order: deterministic
+#pragma unroll
+  for (int t = 0; t < (STRIDE - R0) / 3; ++t)
+    if (t < r_tiles) {
+      r += row[R0 + 3 * t + 0];
+      g += row[R0 + 3 * t + 1];
+      b += row[R0 + 3 * t + 2];
+    }
+  reinterpret_cast<float4*>(raw)[p] = make_float4(r + b_rgb[0], g + b_rgb[1], b + b_rgb[2], a + b_alpha[0]);
+}
+
 cudaError_t launch_finalize_raw(const float* hp, int stride, int a_slot0, int a_tiles, int r_slot0, int r_tiles,
                                 const float* b_alpha, const float* b_rgb, float* raw, int64_t P, cudaStream_t s) {
   if (P == 0) return cudaSuccess;
-  finalize_raw_kernel<<<static_cast<unsigned>((P + 255) / 256), 256, 0, s>>>(hp, stride, a_slot0, a_tiles, r_slot0,
-                                                                            r_tiles, b_alpha, b_rgb, raw, P);
+  const unsigned grid = static_cast<unsigned>((P + 255) / 256);
+  const bool vec = stride == 32 && a_slot0 == 0 && r_slot0 == 8 && a_tiles <= 8 && r_tiles <= 8 &&
+                   (reinterpret_cast<uintptr_t>(hp) & 15u) == 0;
+  if (vec)
+    finalize_raw_vec_kernel<32, 0, 8><<<grid, 256, 0, s>>>(hp, a_tiles, r_tiles, b_alpha, b_rgb, raw, P);
+  else
+    finalize_raw_kernel<<<grid, 256, 0, s>>>(hp, stride, a_slot0, a_tiles, r_slot0, r_tiles, b_alpha, b_rgb, raw, P);
   return cudaGetLastError();
 }
 
