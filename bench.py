@@ -236,7 +236,7 @@ def run_reference(args, rank, world):
     val = n / (ms / 1e3)
     sample = (f"{n} rays of the {args.H}x{args.W} frame per step, fp32 PyTorch (oracle port), {cores} torch threads "
               f"(fastest of all/half/quarter/eighth of {logical} logical CPUs)")
-    line = {"impl": "reference", "metric": "rays/sec at 800x800x64 samples (FULL: 64 coarse + 128 fine evaluations/ray)",
+    line = {"impl": "reference", "metric": metric_name(args),
             "value": val, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(args),
@@ -245,9 +245,24 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def fine_evals(args):
+    """Fine-net evaluations per ray: the reference runs the fine pass on all N_samples + N_importance points, or not at
+    all when N_importance == 0 (render_class.py:321) — SURVEY §8(d)'s COARSE64 pipeline."""
+    return args.n_samples + args.n_importance if args.n_importance > 0 else 0
+
+
+def metric_name(args):
+    if args.n_importance > 0:
+        return (f"rays/sec at {args.H}x{args.W}x{args.n_samples} samples (FULL: {args.n_samples} coarse + "
+                f"{fine_evals(args)} fine evaluations/ray)")
+    return f"rays/sec at {args.H}x{args.W}x{args.n_samples} samples (COARSE{args.n_samples}: coarse net only, N_importance=0)"
+
+
 def workload_config(args):
-    return {"workload": f"{args.H}x{args.W} frame ({args.H * args.W} rays), FULL pipeline: N_samples={args.n_samples} "
-                        f"coarse (D=8,W=256) + {args.n_samples + args.n_importance} fine (D=10,W=1024) evaluations per ray, "
+    pipe = (f"FULL pipeline: N_samples={args.n_samples} coarse (D=8,W=256) + {fine_evals(args)} fine (D=10,W=1024) "
+            "evaluations per ray") if args.n_importance > 0 else \
+        f"COARSE{args.n_samples} pipeline: N_samples={args.n_samples} coarse (D=8,W=256) evaluations per ray, no fine pass"
+    return {"workload": f"{args.H}x{args.W} frame ({args.H * args.W} rays), {pipe}, "
                         "single identity, perturb=0 (render_kwargs_test)",
             "rays_per_step": args.H * args.W, "parallelism": f"ray-sharded x{args.gpus}",
             "l2": "working set (activation buffers, >1 GB per pass) >> 126 MB L2; 256 MB scratch write between timed steps"}
@@ -448,9 +463,14 @@ def main():
         except Exception:
             traffic = None
     n_loc = hi - lo
-    flop_step = n_loc * (args.n_samples * FLOP_COARSE_PT + (args.n_samples + args.n_importance) * FLOP_FINE_PT)
+    flop_step = n_loc * (args.n_samples * FLOP_COARSE_PT + fine_evals(args) * FLOP_FINE_PT)
+    dom, dom_name = fine_p, "dense_tc2_kernel<6,0,8,1> (fine-net layers; tcgen05.mma.cta_group::2 kind::f16, 256x256 pair tiles)"
+    if fine_p["ms"] <= 0:        # COARSE64: the only dense work is the fused coarse kernel
+        dom, dom_name = prof[0], "coarse_fused_kernel (whole coarse net per launch; tcgen05.mma kind::f16, activations in smem)"
+        ach_tf = (dom["algo_flops"] / (dom["ms"] / 1e3)) / 1e12 if dom["ms"] > 0 else 0.0
+        traffic = None
     line = {
-        "metric": "rays/sec at 800x800x64 samples (FULL: 64 coarse + 128 fine evaluations/ray)",
+        "metric": metric_name(args),
         "value": rays_per_s, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f16 operands / f32 accumulate (dense layers); f32 elsewhere", "data": "synthetic",
@@ -460,12 +480,12 @@ def main():
                 "h2d_bytes_per_step": int(n_loc * 6 * 4), "d2h_bytes_per_step": int(n_total * 3 * 4),
                 "api": "B200Renderer.render_fitting(rays=pinned host tensors) -> rgb copied to pinned host"},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "tensor", "kernel": "dense_tc2_kernel<6> (fine-net layers; tcgen05.mma.cta_group::2 kind::f16, 256x256 pair tiles)",
+        "roofline": {"bound": "tensor", "kernel": dom_name,
                      "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
                      "peak_source": peak_src, "traffic": traffic,
-                     "launches_per_step": fine_p["launches"] // max(1, args.steps),
-                     "avg_launch_ms": fine_p["ms"] / max(1, fine_p["launches"]),
-                     "kernel_share_of_step": fine_p["ms"] / (ms_dev * args.steps),
+                     "launches_per_step": dom["launches"] // max(1, args.steps),
+                     "avg_launch_ms": dom["ms"] / max(1, dom["launches"]),
+                     "kernel_share_of_step": dom["ms"] / (ms_dev * args.steps),
                      "coarse_dense": {"tflops": (prof[0]["algo_flops"] / (prof[0]["ms"] / 1e3)) / 1e12 if prof[0]["ms"] > 0 else 0.0,
                                       "share_of_step": prof[0]["ms"] / (ms_dev * args.steps)},
                      "whole_step_tflops": flop_step / (ms_dev / 1e3) / 1e12},
