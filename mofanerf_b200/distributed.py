@@ -2,7 +2,12 @@
 
 Rays are independent given (weights, latents): rank r of R renders the contiguous row-major range
 [r*ceil(N/R), (r+1)*ceil(N/R)) and one all-gather of the per-rank RGB tile rebuilds the image —
-the only collective on the path (NCCL over NVLink on the GPU box; gloo in the CPU tests).
+the only collective on the rendering path (NCCL over NVLink on the GPU box; gloo in the CPU tests).
+
+Training is the one place the path has a real exchange step: each rank draws its own N_rand rays
+(run_train.py:318-331), and the weight gradients the backward kernels leave in `param.grad` are averaged across ranks
+before the optimiser step — `allreduce_gradients` below, bucketed so that the ~116 MB of fp32 gradients (29 M NeRF
+parameters) go out as a few large collectives instead of one per tensor.
 """
 from __future__ import annotations
 
@@ -49,3 +54,42 @@ def render_sharded(render_fn: Callable[[torch.Tensor], Dict[str, torch.Tensor]],
         else:
             out[k + "_local"] = v
     return out
+
+
+def allreduce_gradients(params: Iterable[torch.Tensor], group=None, bucket_bytes: int = 32 << 20,
+                        average: bool = True) -> int:
+    """Sum (or average) `p.grad` over the ranks of `group`, in place.  Gradients are packed into flat buckets of about
+    `bucket_bytes` per (device, dtype) — NVSwitch makes the cost per collective launch-bound, not link-bound, so few
+    large buckets beat one all-reduce per tensor.  Parameters whose grad is None on this rank contribute zeros (every
+    rank must walk the same parameter list: the reference's optimiser groups, create_model_condition.py:55-60).
+    Returns the number of collectives issued."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return 0
+    world = dist.get_world_size(group)
+    if world == 1:
+        return 0
+    params = [p for p in params if p.requires_grad]
+    calls = 0
+    i = 0
+    while i < len(params):
+        key = (params[i].device, params[i].dtype)
+        bucket, nbytes = [], 0
+        while i < len(params) and (params[i].device, params[i].dtype) == key and (not bucket or nbytes < bucket_bytes):
+            bucket.append(params[i])
+            nbytes += params[i].numel() * params[i].element_size()
+            i += 1
+        flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in bucket])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        if average:
+            flat.div_(world)
+        off = 0
+        for p in bucket:
+            n = p.numel()
+            g = flat[off:off + n].view_as(p)
+            if p.grad is None:
+                p.grad = g.clone()
+            else:
+                p.grad.copy_(g)
+            off += n
+        calls += 1
+    return calls

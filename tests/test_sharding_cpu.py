@@ -56,3 +56,41 @@ def test_two_rank_gloo_allgather_rebuilds_row_major_order():
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, True), (1, True)]
+
+
+def _grad_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mofanerf_b200.distributed import allreduce_gradients
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(7, 33), torch.nn.ReLU(), torch.nn.Linear(33, 5))   # same init on every rank
+    frozen = torch.nn.Parameter(torch.ones(3), requires_grad=False)
+    x = torch.full((4, 7), float(rank + 1))
+    net(x).sum().backward()
+    net[2].bias.grad = None                       # a parameter one rank did not touch
+    local = [None if p.grad is None else p.grad.clone() for p in net.parameters()]
+    # tiny buckets: several collectives, bucket boundaries inside the parameter list
+    calls = allreduce_gradients(list(net.parameters()) + [frozen], bucket_bytes=256)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, local)
+    ok = calls >= 2 and frozen.grad is None
+    for j, p in enumerate(net.parameters()):
+        want = sum((g[j] if g[j] is not None else torch.zeros_like(p)) for g in gathered) / world
+        ok = ok and p.grad is not None and torch.allclose(p.grad, want, rtol=1e-6, atol=1e-7)
+    q.put((rank, bool(ok)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_gradient_average_matches_manual_sum():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_grad_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]
