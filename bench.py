@@ -176,7 +176,7 @@ def cpu_baseline(n_s, n_i, sample_rays, max_seconds=25.0):
         n = min(4096, int(n * max(2.0, min(8.0, 10.0 / max(dt, 1e-3)))))
     n, dt = best
     return {"value": n / dt, "unit": "rays/s", "cores": cores, "kind": "port",
-            "sample": f"{n} rays x ({n_s} coarse + {n_s + n_i} fine) samples, fp32, oracle/mofa_oracle.py, {dt:.1f} s, "
+            "sample": f"{n} rays x ({n_s} coarse + {n_s + n_i if n_i > 0 else 0} fine) samples, fp32, oracle/mofa_oracle.py, {dt:.1f} s, "
                       f"{cores} torch threads (fastest of all/half/quarter/eighth of {logical} logical CPUs)"}
 
 
@@ -188,7 +188,7 @@ def torch_gpu_baseline(n_s, n_i, dev, n_rays=8192):
     c, f, s = c.to(dev), f.to(dev), s.to(dev)
     shape, tex, exp, ro, rd = synth_inputs(128, 128)
     idx = torch.linspace(0, ro.shape[0] - 1, n_rays).long()
-    out = {"sample": f"{n_rays} rays x ({n_s} coarse + {n_s + n_i} fine) samples, oracle port on cuda, netchunk 65536"}
+    out = {"sample": f"{n_rays} rays x ({n_s} coarse + {n_s + n_i if n_i > 0 else 0} fine) samples, oracle port on cuda, netchunk 65536"}
     with torch.no_grad(), torch.device(dev):
         rays = O.make_ray_batch(ro[idx].to(dev), rd[idx].to(dev), 8.0, 26.0)
         shape, tex, exp = shape.to(dev), tex.to(dev), exp.to(dev)
