@@ -49,9 +49,10 @@ def parse():
     ap.add_argument("--chunk-rays", type=int, default=0, help="engine-internal rays per pass (0 = default)")
     ap.add_argument("--cpu-sample-rays", type=int, default=0, help="rays in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--torch-gpu-baseline", action="store_true",
-                    help="also time the reference algorithm (fp32 PyTorch port) on this GPU, the denominator of the "
-                         "north_star's '>=10x the reference single-GPU PyTorch path'; opt-in, adds 'torch_gpu_baseline'")
+    ap.add_argument("--no-torch-gpu-baseline", action="store_true",
+                    help="skip timing the reference algorithm (fp32 / TF32 PyTorch eager port) on this GPU — the denominator "
+                         "of the north_star's '>=10x the reference single-GPU PyTorch path' (part of the default N=1 line)")
+    ap.add_argument("--torch-gpu-baseline", action="store_true", help=argparse.SUPPRESS)   # round-1 flag, now the default
     ap.add_argument("--workload", default="frame", choices=["frame", "fit", "train"],
                     help="frame: BASELINE metric (800x800 FULL render); fit: run_fit.py iteration (1024 rays, fwd+bwd+Adam)")
     return ap.parse_args()
@@ -180,15 +181,17 @@ def cpu_baseline(n_s, n_i, sample_rays, max_seconds=25.0):
                       f"{cores} torch threads (fastest of all/half/quarter/eighth of {logical} logical CPUs)"}
 
 
-def torch_gpu_baseline(n_s, n_i, dev, n_rays=8192):
-    """The reference algorithm as PyTorch eager kernels on the same B200 (fp32 cuBLAS, then with TF32 allowed):
-    context for the speed-up, not a target.  Uses the oracle port because /root/reference is absent on the GPU box."""
+def torch_gpu_baseline(n_s, n_i, dev, n_rays=8192, netchunk=196608):
+    """The reference algorithm as PyTorch eager kernels on the same B200 (fp32 cuBLAS, then with TF32 allowed), at the
+    reference's default netchunk (configs/exp_mofanerf.txt): the denominator of '>=10x the reference single-GPU PyTorch
+    path' (BASELINE.md §4.1).  Uses the oracle port because /root/reference is absent on the GPU box."""
     from oracle import mofa_oracle as O
     c, f, s = O.build_nets(0)
     c, f, s = c.to(dev), f.to(dev), s.to(dev)
     shape, tex, exp, ro, rd = synth_inputs(128, 128)
     idx = torch.linspace(0, ro.shape[0] - 1, n_rays).long()
-    out = {"sample": f"{n_rays} rays x ({n_s} coarse + {n_s + n_i if n_i > 0 else 0} fine) samples, oracle port on cuda, netchunk 65536"}
+    out = {"sample": f"{n_rays} rays x ({n_s} coarse + {n_s + n_i if n_i > 0 else 0} fine) samples per timed pass, oracle port "
+                     f"(oracle/mofa_oracle.py) on cuda under torch.no_grad(), netchunk {netchunk}, 2 warm-up + 3 timed passes"}
     with torch.no_grad(), torch.device(dev):
         rays = O.make_ray_batch(ro[idx].to(dev), rd[idx].to(dev), 8.0, 26.0)
         shape, tex, exp = shape.to(dev), tex.to(dev), exp.to(dev)
@@ -196,11 +199,11 @@ def torch_gpu_baseline(n_s, n_i, dev, n_rays=8192):
         for name, tf32 in (("fp32", False), ("tf32", True)):
             torch.backends.cuda.matmul.allow_tf32 = tf32
             for _ in range(2):
-                O.render_rays(rays, c, f, shape, em, tex, N_samples=n_s, N_importance=n_i)
+                O.render_rays(rays, c, f, shape, em, tex, N_samples=n_s, N_importance=n_i, netchunk=netchunk)
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             for _ in range(3):
-                O.render_rays(rays, c, f, shape, em, tex, N_samples=n_s, N_importance=n_i)
+                O.render_rays(rays, c, f, shape, em, tex, N_samples=n_s, N_importance=n_i, netchunk=netchunk)
             torch.cuda.synchronize()
             out[f"rays_per_s_{name}"] = 3 * n_rays / (time.perf_counter() - t0)
     torch.backends.cuda.matmul.allow_tf32 = False
@@ -222,7 +225,7 @@ def run_reference(args, rank, world):
         with torch.no_grad():
             O.render_rays(cal, c, f, shape, em, tex, N_samples=args.n_samples, N_importance=args.n_importance)
     cores, logical = pick_threads(_cal)
-    n = args.cpu_sample_rays if args.cpu_sample_rays > 0 else 128
+    n = args.cpu_sample_rays if args.cpu_sample_rays > 0 else 1024
     idx = torch.linspace(0, ro.shape[0] - 1, n).long()
     rays = O.make_ray_batch(ro[idx], rd[idx], 8.0, 26.0)
     times = []
@@ -234,12 +237,16 @@ def run_reference(args, rank, world):
             times.append(time.perf_counter() - t0)
     ms = 1e3 * sum(times) / len(times)
     val = n / (ms / 1e3)
-    sample = (f"{n} rays of the {args.H}x{args.W} frame per step, fp32 PyTorch (oracle port), {cores} torch threads "
-              f"(fastest of all/half/quarter/eighth of {logical} logical CPUs)")
+    sample = (f"{n} rays of the {args.H}x{args.W} frame per step (every {ro.shape[0] // n}-th ray of the row-major frame; cost per "
+              f"ray is data-independent, so rays/s extrapolates to the frame), fp32 PyTorch (oracle port of the reference "
+              f"algorithm, kind=port), {cores} torch threads (fastest of all/half/quarter/eighth of {logical} logical CPUs)")
+    cfg = workload_config(args)
+    cfg["reference_arm"] = ("CPU arm: the oracle port (oracle/mofa_oracle.py, fp32 PyTorch restatement pinned to the unmodified "
+                            f"reference by tests/golden) timed on {n} sampled rays per step, not the whole frame")
     line = {"impl": "reference", "metric": metric_name(args),
             "value": val, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": workload_config(args),
+            "data": "synthetic", "config": cfg,
             "cpu_baseline": {"value": val, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -444,6 +451,23 @@ def main():
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
 
+    # ---- outside the timed region: the gathered image of the N-rank run must equal a single-GPU render of the same
+    # rays bit for bit (rank 0 renders a subsample that touches every rank's range on its own GPU)
+    mg_check = None
+    if world > 1:
+        gathered = step_device()
+        n_chk = 2048
+        idx = torch.linspace(0, n_total - 1, n_chk).long()
+        if rank == 0:
+            with torch.no_grad():
+                alone = renderer.render_fitting(1, n_chk, None, chunk=1 << 30, rays=(ro[idx].to(dev), rd[idx].to(dev)),
+                                                shapeCodes=shape_d, uvCodes=tex_d, expType=20, expCodes=exp_d, **kw)[0]
+            same = bool(torch.equal(alone.reshape(-1, 3), gathered.reshape(-1, 3)[idx.to(dev)]))
+            touched = sorted({int(i) // ((n_total + world - 1) // world) for i in idx.tolist()})
+            mg_check = {"rays": n_chk, "ranks_touched": len(touched), "bit_exact_vs_single_gpu": same}
+            if not same:
+                raise SystemExit(f"multi-GPU check FAILED: gathered rgb of the {world}-rank run differs from rank 0's "
+                                 f"single-GPU render of the same {n_chk} rays")
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -492,8 +516,13 @@ def main():
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args.n_samples, args.n_importance, args.cpu_sample_rays)
-    if world == 1 and args.torch_gpu_baseline:
-        line["torch_gpu_baseline"] = torch_gpu_baseline(args.n_samples, args.n_importance, dev)
+    if mg_check is not None:
+        line["multi_gpu_check"] = mg_check
+    if world == 1 and not args.no_torch_gpu_baseline:
+        tg = torch_gpu_baseline(args.n_samples, args.n_importance, dev)
+        tg["speedup_vs_fp32"] = rays_per_s / tg["rays_per_s_fp32"]
+        tg["speedup_vs_tf32"] = rays_per_s / tg["rays_per_s_tf32"]
+        line["torch_gpu_baseline"] = tg
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

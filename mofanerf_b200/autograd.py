@@ -26,6 +26,9 @@ class RenderRaysFn(torch.autograd.Function):
         if cfg["raw_noise_std"] > 0 and cfg.get("noise_c") is None:
             raise NotImplementedError("training-mode render with in-kernel sigma noise: pass explicit noise tensors")
         ctx.engine, ctx.cfg = engine, cfg
+        # backward re-uses the engine's packed weights and folded latents: remember which ones this forward used
+        ctx.latents = tuple(t.detach().clone() for t in (shape, exp_mod, tex))
+        ctx.net_keys = dict(engine._net_keys)
         ctx.param_shapes = [tuple(p.shape) for p in params]
         ctx.n_coarse = cfg.get("n_params_coarse", 0)
         ctx.saved = {k: out.pop(k) for k in ("_train_ws", "_rays", "_noise")}
@@ -38,6 +41,15 @@ class RenderRaysFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, *grads):
+        if ctx.saved is None:
+            raise RuntimeError("mofanerf_b200: backward called twice on the same render (activations are released after "
+                               "the first backward; retain_graph is not supported)")
+        eng = ctx.engine
+        for which in (0, 1):
+            if ctx.net_keys[which] is not None and eng._net_keys[which] != ctx.net_keys[which]:
+                raise RuntimeError("mofanerf_b200: network weights were changed or replaced between forward and backward of "
+                                   "a render (load_network / optimizer step): the saved activations no longer match")
+        eng.set_latents(*ctx.latents)     # another render may have folded other codes since the forward
         g = dict(zip(ctx.keys, grads))
         d_rgb, d_acc = g.get("rgb_map"), g.get("acc_map")
         d_rgb0, d_acc0 = g.get("rgb0"), g.get("acc0")

@@ -997,7 +997,7 @@ int run_backward(mofa_b200_ctx* c, Net& net, const TrainWS& t, const PassBufs& p
     DenseLaunch d;
     memset(&d, 0, sizeof(d));
     int nseg = 0;
-    for (int cidx = 0; cidx < nd && nseg < 2; ++cidx) {
+    for (int cidx = 0; cidx < nd; ++cidx) {
       const Step& cs = *dense[cidx];
       const Layer& CL = net.layers[cs.layer];
       for (int i = 0; i < CL.nseg; ++i) {
@@ -1041,6 +1041,8 @@ int run_backward(mofa_b200_ctx* c, Net& net, const TrainWS& t, const PassBufs& p
     if (st.head == 2) {   // view layer: only rgb_linear consumes it
       CK(launch_view_head_bwd(t.d_raw, net.w_rgb, pb.act[k], L.N, P_rows, t.dz[k], s));
       c->launches++;
+      if (M > P_rows)     // padding rows feed the dX GEMMs and the weight-gradient reduction: must be zero, not stale
+        CK(cudaMemsetAsync(t.dz[k] + P_rows * L.N, 0, sizeof(__half) * (size_t)(M - P_rows) * L.N, s));
     } else {
       if (gemm(k, L.N, t.dz[k], pb.act[k], st.head == 1)) return 1;
     }
@@ -1124,6 +1126,9 @@ int mofa_b200_render_rays_train_fwd(mofa_b200_ctx* c, const mofa_b200_render_arg
   if (fine && (a->fine_net < 0 || a->fine_net > 1 || !c->nets[a->fine_net].loaded))
     return fail("train_fwd: fine network not loaded");
   Net* nf = fine ? &c->nets[a->fine_net] : nullptr;
+  if (nc.W > 1024 || (nf && nf->W > 1024))
+    return fail("train_fwd: networks wider than 1024 are not supported in training mode (the unfused head path reads the "
+                "ping-pong buffers, which the activation-keeping forward does not write)");
   if (!c->latents_set) return fail("train_fwd: set_latents has not been called");
   CK(cudaSetDevice(c->device));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -1137,6 +1142,17 @@ int mofa_b200_render_rays_train_fwd(mofa_b200_ctx* c, const mofa_b200_render_arg
   const int lindisp = (a->flags & MOFA_FLAG_LINDISP) ? 1 : 0;
   const int white = (a->flags & MOFA_FLAG_WHITE_BKGD) ? 1 : 0;
   Workspace ws = t.fw;
+  // Rows [n*S, round_up(n*S, 128)) of the encodings are read by the dense layers and by the weight-gradient GEMM (which
+  // reduces over all padded rows) but never written by encode_rays: zero them so every padding row of every activation
+  // stays finite (the workspace is uninitialised allocator memory).
+  for (int ps = 0; ps < (fine ? 2 : 1); ++ps) {
+    const int64_t rows = n * (ps == 0 ? S_c : S_f);
+    const int64_t pad = (rows + 127) / 128 * 128 - rows;
+    if (pad > 0) {
+      CK(cudaMemsetAsync(t.pass[ps].X0 + rows * 64, 0, sizeof(__half) * 64 * pad, s));
+      CK(cudaMemsetAsync(t.pass[ps].V + rows * 64, 0, sizeof(__half) * 64 * pad, s));
+    }
+  }
   // ---- coarse pass (activations kept)
   ws.X0 = t.pass[0].X0;
   ws.V = t.pass[0].V;
@@ -1212,6 +1228,10 @@ int mofa_b200_render_rays_bwd(mofa_b200_ctx* c, const mofa_b200_bwd_args* a, voi
     CK(launch_composite_bwd(t.pass[ps].raw, t.pass[ps].z, a->rays, a->ray_stride, noise, g_rgb, g_acc, scale, n, S, white,
                             t.d_raw, a->d_rays, s));
     c->launches++;
+    {
+      const int64_t rows = n * S, pad = (rows + 127) / 128 * 128 - rows;
+      if (pad > 0) CK(cudaMemsetAsync(t.d_raw + rows * 4, 0, sizeof(float) * 4 * pad, s));   // rank-1 sigma term of padding rows
+    }
     float* const* dp = (&net == &nc) ? a->d_params_coarse : a->d_params_fine;
     if (dp && (&net == &nc ? a->n_params_coarse : a->n_params_fine) != 2 * (n_dense_steps(net) + 2))
       return fail("bwd: d_params has the wrong number of tensors");

@@ -37,22 +37,35 @@ def all_gather_rows(local: torch.Tensor, n_total: int, group=None) -> torch.Tens
 
 
 def render_sharded(render_fn: Callable[[torch.Tensor], Dict[str, torch.Tensor]], rays: torch.Tensor,
-                   keys: Iterable[str] = ("rgb_map",), group=None) -> Dict[str, torch.Tensor]:
-    """Run `render_fn` on this rank's ray range and all-gather `keys` (default: the RGB tile only, as
-    BASELINE.json's north_star specifies).  Keys not gathered are returned for the local range only,
-    under '<key>_local'."""
+                   group=None, max_floats_per_ray: int = 32) -> Dict[str, torch.Tensor]:
+    """Run `render_fn` on this rank's ray range and rebuild every per-ray output on every rank with ONE all-gather:
+    the keys render_rays returns (rgb_map, disp_map, acc_map, rgb0, disp0, acc0, z_std: 11 floats per ray) are packed
+    side by side into a single [N/R, C] tile, gathered, and unpacked — the RGB tile BASELINE.json's north_star names plus
+    the reference's extras in the same collective (28 MB per 800x800 frame).  Per-sample outputs (`raw`, weights) are
+    refused here: gathering [N, S, 4] is not what the sharded mode is for."""
     if not (dist.is_available() and dist.is_initialized()):
         return render_fn(rays)
     n = rays.shape[0]
     lo, hi = shard_range(n, dist.get_rank(group), dist.get_world_size(group))
     local = render_fn(rays[lo:hi])
-    out = {}
-    keys = tuple(keys)
-    for k, v in local.items():
-        if k in keys:
-            out[k] = all_gather_rows(v, n, group)
-        else:
-            out[k + "_local"] = v
+    keys = sorted(local.keys())
+    widths = []
+    for k in keys:
+        v = local[k]
+        w = int(v[0].numel()) if v.shape[0] > 0 else int(torch.tensor(v.shape[1:]).prod().item()) if v.dim() > 1 else 1
+        if v.requires_grad:
+            raise RuntimeError("ray-sharded rendering is inference only (the all-gather is not differentiable)")
+        widths.append(w)
+    if sum(widths) > max_floats_per_ray:
+        big = [k for k, w in zip(keys, widths) if w > 16]
+        raise RuntimeError(f"ray-sharded rendering cannot return per-sample outputs {big}: render those without "
+                           "MOFA_B200_SHARD or on one rank")
+    packed = torch.cat([local[k].reshape(hi - lo, -1).float() for k in keys], 1)
+    full = all_gather_rows(packed, n, group)
+    out, c0 = {}, 0
+    for k, w in zip(keys, widths):
+        out[k] = full[:, c0:c0 + w].reshape((n,) + tuple(local[k].shape[1:]))
+        c0 += w
     return out
 
 

@@ -319,7 +319,9 @@ def get_engine(device=None) -> Engine:
     """Process-wide engine per CUDA device."""
     if not torch.cuda.is_available():
         raise RuntimeError("mofanerf_b200 needs a CUDA device (sm_100a); there is no CPU path")
-    idx = torch.cuda.current_device() if device is None else (torch.device(device).index or 0)
+    idx = None if device is None else torch.device(device).index
+    if idx is None:        # a bare "cuda" means the current device, not GPU 0
+        idx = torch.cuda.current_device()
     if idx not in _engines:
         _engines[idx] = Engine(torch.device("cuda", idx))
     return _engines[idx]

@@ -249,14 +249,18 @@ class B200Renderer(torch.nn.Module):
     def _render_all(self, chunk, sh, **kwargs):
         if self.shard_rays and torch.distributed.is_available() and torch.distributed.is_initialized():
             full = self.rays
+            if _needs_grad(full, self.shapeCodes, self.decoding_texCodes, self.expCodes_Sigma[self.expType]):
+                raise RuntimeError("MOFA_B200_SHARD=1 shards the rays of ONE image for inference; fitting / training need "
+                                   "gradients: run them data-parallel (distributed.allreduce_gradients) instead")
 
             def local_fn(r):
                 self.rays = r
                 return self.batchify_rays(chunk, **kwargs)
 
-            out = mdist.render_sharded(local_fn, full, keys=("rgb_map", "disp_map", "acc_map"))
-            self.rays = full
-            all_ret = {k: v for k, v in out.items() if not k.endswith("_local")}
+            try:
+                all_ret = mdist.render_sharded(local_fn, full)
+            finally:
+                self.rays = full
         else:
             all_ret = self.batchify_rays(chunk, **kwargs)
         return self._finish(all_ret, sh)

@@ -155,8 +155,85 @@ def op_cases():
     print("[golden] ops.npz written")
 
 
+def frame_crop_cases():
+    """Round-2 fixtures: crops of the 800x800 frame at the real widths (W_f = 1024) for BASELINE configs #4 and #5.
+
+    cfg4 (run_fit.py:394-403, rendering_modulation): render_fitting with expCodes = render.expCodes_Sigma[e] for three
+    expression slots, same identity, target_pose = pose_spherical(0, 0, 16).
+    cfg5 (render_refine_trainSet.py:245-304 -> render_path -> render, models/render_class.py:125-197): three identities,
+    each with its own shape code, its own 512x512 UV map through the (seeded random-init) texture encoder, its own
+    expression slot and view.
+    The rays are a seeded random subset of the frame's 640 000 rays (indices stored: the engine's in-kernel ray
+    generation must reproduce them from (c2w, K, H, W))."""
+    ref = ref_loader.load()
+    seed, W_c, D_c, W_f, D_f, H, W, n_crop = 5, 256, 8, 1024, 10, 800, 800, 192
+    coarse, fine, renderer = ref_loader.build_reference(seed, W_c, D_c, W_f, D_f)
+    oc, of, ostyle = O.build_nets(seed, W_c, D_c, W_f, D_f)
+    _check_same_nets(coarse, oc)
+    _check_same_nets(fine, of)
+    _check_same_nets(renderer.idSpecificMod, ostyle)
+    exp_table = torch.cat([c.detach().reshape(1, 30) for c in renderer.expCodes_Sigma[:20]], 0)
+    # the GPU tests rebuild the texture encoder and the expression table from the seed (tests/helpers.py
+    # build_reference_like): make sure that rebuild is bit-identical to the reference's own construction
+    from tests.helpers import build_reference_like
+    _, _, _, mine = build_reference_like(seed, W_c, D_c, W_f, D_f)
+    _check_same_nets(renderer.texEncoder, mine.texEncoder)
+    _check_same_nets(renderer.idSpecificMod, mine.idSpecificMod)
+    assert all(torch.equal(a.cpu(), b.cpu()) for a, b in zip(renderer.expCodes_Sigma[:20], mine.expCodes_Sigma[:20]))
+    kwargs = dict(network_fn=coarse, network_fine=fine, N_samples=64, N_importance=64, perturb=0.0, raw_noise_std=0.0,
+                  white_bkgd=False, lindisp=False, use_viewdirs=True, ndc=False, near=8.0, far=26.0, retraw=False)
+    meta = dict(seed=seed, W_c=W_c, D_c=D_c, W_f=W_f, D_f=D_f, H=H, W=W, N_samples=64, N_importance=64, perturb=0.0,
+                raw_noise_std=0.0, pytest=0, white_bkgd=0, lindisp=0, sigma_bias=np.nan, near=8.0, far=26.0)
+
+    def save(name, out, extras, rays_o, rays_d, idx, K, c2w, shape, tex, exp, **more):
+        res = dict(rgb_map=out[0], disp_map=out[1], acc_map=out[2])
+        for k in ("rgb0", "disp0", "acc0", "z_std"):
+            res[k] = extras[k]
+        arrays = {f"out_{k}": v.detach().numpy().astype(np.float32) for k, v in res.items()}
+        arrays.update(rays_o=rays_o.numpy(), rays_d=rays_d.numpy(), ray_index=idx.numpy(), K=K, c2w=c2w.numpy(),
+                      shape=shape.numpy(), tex=tex.detach().numpy(), exp=exp.detach().numpy(), exp_table=exp_table.numpy())
+        for k, v in more.items():
+            arrays[k] = np.asarray(v)
+        for k, v in meta.items():
+            arrays[f"meta_{k}"] = np.asarray(v)
+        np.savez_compressed(os.path.join(OUT, f"{name}.npz"), **arrays)
+        print(f"[golden] {name}: rays={rays_o.shape[0]} rgb mean={arrays['out_rgb_map'].mean():.4f} "
+              f"acc mean={arrays['out_acc_map'].mean():.4f}")
+
+    # ---- config #4: expression sweep (three of the slots run_fit.py:394 renders)
+    shape, tex, exp_unused = _latents(seed + 100)
+    K, c2w = _camera(H, W, 0.0)
+    ro, rd = ref.helpers.get_rays(H, W, K, c2w[:3, :4])
+    ro, rd = ro.reshape(-1, 3), rd.reshape(-1, 3)
+    for e in (9, 14, 2):
+        idx = torch.randperm(H * W, generator=torch.Generator().manual_seed(1000 + e))[:n_crop].sort()[0]
+        with torch.no_grad():
+            out = renderer.render_fitting(H, W, K, chunk=4096, rays=(ro[idx], rd[idx]), shapeCodes=shape, uvCodes=tex,
+                                          expType=20, expCodes=renderer.expCodes_Sigma[e], **kwargs)
+        save(f"cfg4_800_exp{e}", out[:3], out[3], ro[idx], rd[idx], idx, K, c2w, shape, tex,
+             renderer.expCodes_Sigma[e], exp_slot=e)
+
+    # ---- config #5: identities through render() with a UV map -> texEncoder
+    for i, (angle, e) in enumerate(((-35.0, 3), (0.0, 11), (50.0, 17))):
+        shape_i, _, _ = _latents(seed + 200 + i)
+        uv = torch.rand(512, 512, 3, generator=torch.Generator().manual_seed(300 + i))
+        K, c2w = _camera(H, W, angle)
+        ro, rd = ref.helpers.get_rays(H, W, K, c2w[:3, :4])
+        ro, rd = ro.reshape(-1, 3), rd.reshape(-1, 3)
+        idx = torch.randperm(H * W, generator=torch.Generator().manual_seed(2000 + i))[:n_crop].sort()[0]
+        with torch.no_grad():
+            out = renderer.render(H, W, K, chunk=4096, rays=(ro[idx], rd[idx]), shapeCodes=shape_i, uvMap=uv, expType=e,
+                                  **kwargs)
+            tex_i = renderer.decoding_texCodes.reshape(-1)
+        save(f"cfg5_800_id{i}", out[:3], out[3], ro[idx], rd[idx], idx, K, c2w, shape_i, tex_i,
+             renderer.expCodes_Sigma[e], exp_slot=e, uv_seed=300 + i, angle=angle)
+
+
 def main():
     torch.set_num_threads(os.cpu_count())
+    if "--r02" in sys.argv:      # only the round-2 frame crops (the round-1 fixtures are unchanged)
+        frame_crop_cases()
+        return
     op_cases()
     # config #1 (plumbing): 64x64, 32 samples, coarse only
     render_case("cfg1_64x64_s32", 0, 256, 8, 1024, 10, 64, 64, 0.0, 32, 0)
@@ -170,6 +247,7 @@ def main():
     # empty space: negative sigma bias => acc ~ 0, NaN disparity; white background; lindisp
     render_case("empty_white", 4, 256, 8, 256, 10, 16, 16, 20.0, 64, 64, crop=64, white_bkgd=True,
                 sigma_bias=-30.0, lindisp=True)
+    frame_crop_cases()
 
 
 if __name__ == "__main__":

@@ -14,7 +14,32 @@ def load_case(name):
     meta = {k[5:]: z[k].item() for k in z.files if k.startswith("meta_")}
     out = {k[4:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("out_")}
     inp = {k: torch.from_numpy(z[k]) for k in ("rays_o", "rays_d", "shape", "tex", "exp")}
+    for k in ("ray_index", "K", "c2w", "exp_table", "exp_slot", "uv_seed", "angle"):   # round-2 frame crops
+        if k in z.files:
+            inp[k] = torch.from_numpy(z[k]) if z[k].ndim else z[k].item()
     return meta, inp, out
+
+
+FRAME_CROPS_CFG4 = ["cfg4_800_exp9", "cfg4_800_exp14", "cfg4_800_exp2"]
+FRAME_CROPS_CFG5 = ["cfg5_800_id0", "cfg5_800_id1", "cfg5_800_id2"]
+
+
+def build_reference_like(seed, W_c=256, D_c=8, W_f=1024, D_f=10):
+    """(coarse, fine, style, renderer) in the RNG order of oracle/ref_loader.build_reference — which follows
+    tools/create_model_condition.py:16-50 — using the oracle's nets and the product's B200Renderer (whose constructor
+    consumes the generator exactly like myRenderer.__init__, models/render_class.py:41-58: texture encoder, StyleModule,
+    20 expression codes; oracle/make_golden.py asserts this against the reference before writing the cfg5 fixtures)."""
+    from mofanerf_b200 import B200Renderer
+    torch.manual_seed(seed)
+    in_ch, in_v = O.embed_dim(10) + 30, O.embed_dim(4)
+    coarse = O.NeRF(D_c, W_c, in_ch, in_v, 256, 50).eval()
+    fine = O.NeRF(D_f, W_f, in_ch, in_v, 256, 50).eval()
+    state = torch.random.get_rng_state()
+    style = O.StyleModule(input_ch_bm=50, out_ch=30).eval()
+    torch.random.set_rng_state(state)
+    renderer = B200Renderer(expCodesLen=30)
+    renderer.idSpecificMod.load_state_dict(style.state_dict())
+    return coarse, fine, style, renderer.eval()
 
 
 def build_case_nets(meta):

@@ -9,6 +9,7 @@ import pytest
 import torch
 
 from oracle import mofa_oracle as O
+from tests import parity_log
 from tests.helpers import build_case_nets, load_case
 
 pytestmark = pytest.mark.gpu
@@ -58,6 +59,7 @@ def test_render_with_uvmap_matches_oracle():
     d = (rgb.cpu().reshape(-1, 3) - ref["rgb_map"]).abs().max().item()
     d0 = (extras["rgb0"].cpu().reshape(-1, 3) - ref["rgb0"]).abs().max().item()
     print(f"[parity] render(): rgb {d:.2e} rgb0 {d0:.2e}")
+    parity_log.record("render()[c2w + texEncoder, 6x5]", rgb_map_max=d, rgb0_max=d0)
     assert d <= 6e-2 and d0 <= 4e-3
 
 

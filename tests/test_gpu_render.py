@@ -22,7 +22,9 @@ import pytest
 import torch
 
 from oracle import mofa_oracle as O
-from tests.helpers import build_case_nets, case_randoms, load_case, oracle_render
+from tests import parity_log
+from tests.helpers import (FRAME_CROPS_CFG4, FRAME_CROPS_CFG5, build_case_nets, build_reference_like, case_randoms, load_case,
+                           oracle_render)
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -55,6 +57,14 @@ def engine_render(meta, inp, nets, gemm_simt=False, chunk=1024 * 32, want_aux=Fa
 
 def check_maps(name, got, ref, max_rgb=6e-2, mean_rgb=3e-3, min_psnr=40.0, max_acc=3e-2, disp_min_acc=1e-3):
     msgs = []
+    for k in ("rgb_map", "rgb0"):   # measured numbers go to profiles/parity_r02.json before anything is asserted
+        if k in ref:
+            d = (got[k] - ref[k]).abs()
+            parity_log.record(name, **{f"{k}_max": d.max().item(), f"{k}_mean": d.mean().item(),
+                                       f"{k}_psnr_db": O.psnr(got[k], ref[k]), "rays": ref[k].shape[0]})
+    for k in ("acc_map", "acc0"):
+        if k in ref:
+            parity_log.record(name, **{f"{k}_max": (got[k] - ref[k]).abs().max().item()})
     for k in ("rgb_map", "rgb0"):
         if k in ref:
             d = (got[k] - ref[k]).abs()
@@ -97,6 +107,54 @@ def test_against_reference_fixtures(name):
         check_maps(name, got, gold, max_rgb=1e-1, max_acc=1e-1, disp_min_acc=0.3)   # disp = acc/depth: ill-conditioned on faint rays
     else:
         check_maps(name, got, gold)
+
+
+def _crop_kwargs(meta, c, f):
+    return dict(network_fn=c.to(DEV), network_fine=f.to(DEV), N_samples=int(meta["N_samples"]),
+                N_importance=int(meta["N_importance"]), perturb=0.0, raw_noise_std=0.0, white_bkgd=False, lindisp=False,
+                near=float(meta["near"]), far=float(meta["far"]), use_viewdirs=True, ndc=False)
+
+
+def _maps(rgb, disp, acc, extras):
+    out = dict(rgb_map=rgb, disp_map=disp, acc_map=acc, **{k: v for k, v in extras.items() if torch.is_tensor(v)})
+    return {k: v.float().cpu() for k, v in out.items()}
+
+
+@pytest.mark.parametrize("name", FRAME_CROPS_CFG4)
+def test_frame_crop_config4_expression_sweep(name):
+    """BASELINE config #4 (run_fit.py:394-403): render_fitting with expCodes = expCodes_Sigma[e] on 192 rays of the
+    800x800 frame, real widths (W_c 256 / W_f 1024), against the unmodified reference's output."""
+    meta, inp, gold = load_case(name)
+    c, f, s, r = build_reference_like(int(meta["seed"]))
+    r = r.to(DEV)
+    e = int(inp["exp_slot"])
+    assert torch.equal(r.expCodes_Sigma[e].detach().cpu().reshape(-1), inp["exp"].reshape(-1))
+    with torch.no_grad():
+        out = r.render_fitting(int(meta["H"]), int(meta["W"]), inp["K"].numpy(), chunk=1 << 20,
+                               rays=(inp["rays_o"].to(DEV), inp["rays_d"].to(DEV)), shapeCodes=inp["shape"].to(DEV),
+                               uvCodes=inp["tex"].to(DEV), expType=20, expCodes=r.expCodes_Sigma[e], **_crop_kwargs(meta, c, f))
+    torch.cuda.synchronize()
+    check_maps(name, _maps(*out), gold)
+
+
+@pytest.mark.parametrize("name", FRAME_CROPS_CFG5)
+def test_frame_crop_config5_identities_through_render(name):
+    """BASELINE config #5 (render_refine_trainSet.py:245-304 -> render_path -> render): per identity a shape code, a
+    512x512 UV map through the texture encoder, an expression slot and a view; 192 rays of the 800x800 frame."""
+    meta, inp, gold = load_case(name)
+    c, f, s, r = build_reference_like(int(meta["seed"]))
+    r = r.to(DEV)
+    uv = torch.rand(512, 512, 3, generator=torch.Generator().manual_seed(int(inp["uv_seed"])))
+    with torch.no_grad():
+        out = r.render(int(meta["H"]), int(meta["W"]), inp["K"].numpy(), chunk=1 << 20,
+                       rays=(inp["rays_o"].to(DEV), inp["rays_d"].to(DEV)), shapeCodes=inp["shape"].to(DEV),
+                       uvMap=uv.to(DEV), expType=int(inp["exp_slot"]), **_crop_kwargs(meta, c, f))
+        tex = r.decoding_texCodes.reshape(-1).cpu()
+    torch.cuda.synchronize()
+    d_tex = (tex - inp["tex"]).abs().max().item()
+    parity_log.record(name, tex_code_max=d_tex)
+    assert d_tex <= 1e-4, f"texture encoder (cuDNN) vs reference (CPU): {d_tex:.2e}"
+    check_maps(name, _maps(*out), gold)
 
 
 def test_simt_and_tensor_core_paths_agree():
@@ -143,11 +201,13 @@ def test_teacher_forced_stages(name):
         d = (a - b).abs().max().item()
         sc = max(1.0, b.abs().max().item())
         print(f"[parity] {name} teacher-forced raw {nm}: max {d:.3e} (|ref|max {sc:.1f})")
+        parity_log.record(f"{name}[teacher-forced]", **{f"raw_{nm}_max": d, f"raw_{nm}_refmax": sc})
         assert d <= 2e-2 * sc
     d0 = (rgb_c - ref["rgb0"]).abs().max().item()
     d1 = (rgb_f.cpu() - ref["rgb_map"]).abs().max().item()
     dw = (w_f.cpu() - ref["weights"]).abs().max().item()
     print(f"[parity] {name} teacher-forced rgb: coarse {d0:.2e} fine {d1:.2e} weights {dw:.2e}")
+    parity_log.record(f"{name}[teacher-forced]", rgb0_max=d0, rgb_map_max=d1, weights_max=dw)
     assert d0 <= 4e-3 and d1 <= 4e-3
 
 
@@ -164,6 +224,8 @@ def test_stagewise_vs_oracle_and_ray_order():
     assert dz.mean().item() < 2e-2, f"fine sample depths drift: mean {dz.mean().item():.3e}"
     raw_d = (got["raw"] - ref["raw"]).abs()
     print(f"[parity] raw(fine): max {raw_d.max().item():.3e} mean {raw_d.mean().item():.3e}")
+    parity_log.record("full_w1024[stagewise]", z_fine_mean=dz.mean().item(), z_fine_max=dz.max().item(),
+                      raw_fine_max=raw_d.max().item(), raw_fine_mean=raw_d.mean().item())
     # ray order: permute the input rays; outputs must permute identically (bit-exact)
     perm = torch.randperm(inp["rays_o"].shape[0], generator=torch.Generator().manual_seed(0))
     inp2 = dict(inp, rays_o=inp["rays_o"][perm], rays_d=inp["rays_d"][perm])
@@ -194,6 +256,7 @@ def test_run_network_matches_nerf_forward():
     d = (out - ref).abs()
     scale = ref.abs().max().item()
     print(f"[parity] run_network: max {d.max().item():.3e} (|ref|max {scale:.2f})")
+    parity_log.record("run_network[fine W=256]", raw_max=d.max().item(), raw_refmax=scale)
     assert d.max().item() <= 2e-2 * max(1.0, scale)
 
 

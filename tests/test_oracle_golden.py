@@ -8,7 +8,8 @@ import torch
 
 from oracle import mofa_oracle as O
 from oracle import ref_loader
-from tests.helpers import GOLDEN, assert_close_nan, load_case, oracle_render
+from tests.helpers import (FRAME_CROPS_CFG4, FRAME_CROPS_CFG5, GOLDEN, assert_close_nan, build_reference_like, load_case,
+                           oracle_render)
 
 OPS = np.load(f"{GOLDEN}/ops.npz")
 
@@ -69,6 +70,30 @@ def test_render_cases(name):
         else:
             # disparity = 1/depth can be large: relative tolerance there
             assert_close_nan(out[k], g, 1e-4, 1e-4, what=f"{name}:{k}")
+
+
+@pytest.mark.parametrize("name", FRAME_CROPS_CFG4 + FRAME_CROPS_CFG5)
+def test_frame_crops(name):
+    """Round-2 fixtures: crops of the 800x800 frame at W_f = 1024 (BASELINE configs #4 / #5).  The oracle runs the first
+    32 rays of each crop (CPU time); for cfg5 the texture code is recomputed from the UV map with the texture encoder
+    rebuilt from the seed, which also pins that rebuild (the fixture holds the reference's code)."""
+    meta, inp, gold = load_case(name)
+    n = 32
+    sub = dict(inp, rays_o=inp["rays_o"][:n], rays_d=inp["rays_d"][:n])
+    if name in FRAME_CROPS_CFG5:
+        _, _, _, rend = build_reference_like(int(meta["seed"]))
+        uv = torch.rand(512, 512, 3, generator=torch.Generator().manual_seed(int(inp["uv_seed"])))
+        with torch.no_grad():
+            tex, _ = rend.texEncoder(uv.permute(2, 0, 1).unsqueeze(0))
+        assert torch.equal(tex.reshape(-1), inp["tex"]), "texture encoder rebuilt from the seed differs from the reference's"
+        assert torch.equal(rend.expCodes_Sigma[int(inp["exp_slot"])].detach().cpu().reshape(-1), inp["exp"].reshape(-1))
+    assert torch.equal(inp["exp_table"][int(inp["exp_slot"])], inp["exp"].reshape(-1))
+    # ray indices: the stored rays are rows ray_index of get_rays(H, W, K, c2w) (row-major)
+    ro, rd = O.get_rays(int(meta["H"]), int(meta["W"]), inp["K"].numpy(), inp["c2w"][:3, :4])
+    assert torch.equal(rd.reshape(-1, 3)[inp["ray_index"]], inp["rays_d"])
+    out, _, _ = oracle_render(meta, sub)
+    for k, g in gold.items():
+        assert_close_nan(out[k], g[:n], 1e-4, 1e-4, what=f"{name}:{k}")
 
 
 @pytest.mark.skipif(not ref_loader.available(), reason="reference tree not present on this box")

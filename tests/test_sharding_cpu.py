@@ -32,13 +32,24 @@ def _worker(rank, world, port, n, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     rays = torch.arange(n * 11, dtype=torch.float32).reshape(n, 11)
 
-    def fake_render(r):   # stands in for the CUDA engine: rgb row i encodes ray i's identity
-        return {"rgb_map": r[:, :3] * 2.0 + 1.0, "z_std": r[:, 0]}
+    calls = []
 
-    out = render_sharded(fake_render, rays, keys=("rgb_map",))
-    ok = torch.equal(out["rgb_map"], rays[:, :3] * 2.0 + 1.0)
+    def fake_render(r):   # stands in for the CUDA engine: rgb row i encodes ray i's identity
+        calls.append(r.shape[0])
+        return {"rgb_map": r[:, :3] * 2.0 + 1.0, "z_std": r[:, 0], "rgb0": r[:, 3:6] - 1.0, "acc_map": r[:, 7]}
+
+    out = render_sharded(fake_render, rays)
     lo, hi = shard_range(n, rank, world)
-    ok = ok and out["z_std_local"].shape[0] == hi - lo and "z_std" not in out
+    ok = calls == [hi - lo]                                     # this rank rendered only its own range
+    ok = ok and torch.equal(out["rgb_map"], rays[:, :3] * 2.0 + 1.0)
+    # the extras come back complete too (same single collective), in row-major ray order
+    ok = ok and torch.equal(out["z_std"], rays[:, 0]) and torch.equal(out["rgb0"], rays[:, 3:6] - 1.0)
+    ok = ok and out["acc_map"].shape == (n,) and out["rgb0"].shape == (n, 3)
+    try:      # per-sample outputs are refused, loudly
+        render_sharded(lambda r: {"rgb_map": r[:, :3], "raw": r[:, None, :4].expand(-1, 128, -1)}, rays)
+        ok = False
+    except RuntimeError:
+        pass
     q.put((rank, bool(ok)))
     dist.barrier()
     dist.destroy_process_group()
