@@ -71,6 +71,10 @@ struct Layer {
   int BN_t[2] = {256, 256};
   CUtensorMap tmBt[2];           // box rows = BN_t
   CUtensorMap tmBt2[2];          // box rows = 128 (CTA-pair kernel)
+  // split-precision coarse kernel (W == 256 nets only): low image fp16(w - fp16(w)) and half-N boxes for the CTA pair
+  __half* wlo[2] = {nullptr, nullptr};
+  CUtensorMap tmS_hi[2];         // box rows = N / 2
+  CUtensorMap tmS_lo[2];
 };
 
 struct Step {
@@ -93,6 +97,11 @@ struct Net {
   mofa::FusedLayerDesc* fused_layers = nullptr;
   CUtensorMap* fused_wmaps = nullptr;
   int fused_n = 0;
+  // split-precision fused kernel (W == 256 only): layer table, weight maps, fp32 view-direction columns [W/2, 27]
+  mofa::SplitLayerDesc* split_layers = nullptr;
+  CUtensorMap* split_wmaps = nullptr;
+  int split_n = 0;
+  float* w_view = nullptr;
   std::vector<void*> allocs;
 };
 
@@ -107,6 +116,8 @@ struct mofa_b200_ctx {
   bool latents_set = false;
   bool pair_kernel = true;       // cta_group::2 kernel for N % 256 == 0 (MOFA_B200_DENSE_1CTA=1 disables)
   bool fused_coarse = true;      // one persistent kernel for a W == 256 net (MOFA_B200_NO_FUSED_COARSE=1 disables)
+  bool split_coarse = true;      // ... in split precision (fp16 hi+lo, 3 products): MOFA_B200_COARSE_FP16=1 selects the
+                                 // single-fp16 fused kernel of round 1 instead
   int64_t launches = 0;
   // profiling (bench): CUDA-event pairs around every tensor-core dense launch, on the launch stream
   bool profiling = false;
@@ -177,6 +188,13 @@ int build_layer(mofa_b200_ctx* c, Net& net, const LayerSpec& sp, const float* w,
     c->launches++;
     if (make_tmap_2d(c, &L.tmB[i], L.w[i], sp.N, L.K[i], L.K[i], L.BN)) return 1;
     if (make_tmap_2d(c, &L.tmB2[i], L.w[i], sp.N, L.K[i], L.K[i], 128)) return 1;
+    if (net.W == 256) {
+      if (dev_alloc(net, reinterpret_cast<void**>(&L.wlo[i]), sizeof(__half) * (size_t)sp.N * L.K[i])) return 1;
+      CK(launch_pack_weight_lo(w, sp.in_total, sp.seg_c0[i], sp.seg_k[i], L.K[i], sp.N, L.wlo[i], s));
+      c->launches++;
+      if (make_tmap_2d(c, &L.tmS_hi[i], L.w[i], sp.N, L.K[i], L.K[i], sp.N / 2)) return 1;
+      if (make_tmap_2d(c, &L.tmS_lo[i], L.wlo[i], sp.N, L.K[i], L.K[i], sp.N / 2)) return 1;
+    }
     L.rows_t[i] = L.K[i] < 128 ? 128 : L.K[i];
     L.BN_t[i] = (L.rows_t[i] % 256 == 0) ? 256 : 128;
     if (dev_alloc(net, reinterpret_cast<void**>(&L.wt[i]), sizeof(__half) * (size_t)L.rows_t[i] * sp.N)) return 1;
@@ -243,12 +261,107 @@ int fold_net(mofa_b200_ctx* c, Net& net, cudaStream_t s) {
   return 0;
 }
 
+
+// Layer table of the split-precision fused kernel (coarse_split.cu).  Every layer reads the activation resident in shared
+// memory; a skip layer's second operand becomes a "virtual" layer right after the producer of that operand (raw fp32
+// partial product parked in a scratch, added in the skip layer's epilogue), the view layer's view-direction segment
+// becomes a per-ray vector.  Leaves split_n == 0 (the caller falls back to the single-fp16 fused kernel) when the
+// program does not have the shape the kernel's hazard analysis assumes.
+int build_split_table(mofa_b200_ctx* c, Net& net, cudaStream_t s) {
+  std::vector<const Step*> dense;
+  for (const Step& st : net.program)
+    if (st.kind == 0) dense.push_back(&st);
+  struct Pending { int producer, layer, seg; };
+  std::vector<Pending> pend;
+  for (const Step* st : dense) {
+    const Layer& L = net.layers[st->layer];
+    if (L.nseg == 2 && st->in_step[0] != -2 && st->in_step[1] != -2) {
+      const int prim = st->in_step[0] == st->ord - 1 ? 0 : 1;
+      if (st->in_step[prim] != st->ord - 1) return 0;
+      pend.push_back({st->in_step[1 - prim], st->layer, 1 - prim});
+    }
+  }
+  std::vector<SplitLayerDesc> sl;
+  std::vector<CUtensorMap> maps;
+  bool fresh = false, parked = false, ok = true;
+  auto push_maps = [&](const Layer& L, int seg, SplitLayerDesc& d) {
+    d.map_hi = static_cast<int>(maps.size());
+    maps.push_back(L.tmS_hi[seg]);
+    d.map_lo = static_cast<int>(maps.size());
+    maps.push_back(L.tmS_lo[seg]);
+    d.kb = L.K[seg] / 64;
+  };
+  for (const Step* st : dense) {
+    const Layer& L = net.layers[st->layer];
+    SplitLayerDesc d{};
+    d.bias = L.bias_eff;
+    d.n_out = L.N;
+    d.head = st->head;
+    d.store = st->head == 2 ? 0 : 1;
+    int prim = 0;
+    if (L.nseg == 2) {
+      if (st->in_step[0] == -2 || st->in_step[1] == -2) {
+        prim = st->in_step[0] == -2 ? 1 : 0;
+        d.add_ray = 1;
+        if (L.N != 128 || st->head != 2) ok = false;     // the per-ray vector has 128 columns: the view layer
+      } else {
+        prim = st->in_step[0] == st->ord - 1 ? 0 : 1;
+        d.add_park = 1;
+        if (!parked) ok = false;
+        parked = false;
+      }
+    }
+    push_maps(L, prim, d);
+    if (sl.empty()) {
+      if (st->in_step[prim] != -1 || d.kb != 1) ok = false;    // first layer reads the point encoding (one K block)
+    } else {
+      if (st->in_step[prim] != st->ord - 1 || d.kb != 4) ok = false;
+    }
+    if (d.n_out != 256 && !(d.n_out == 128 && !d.store)) ok = false;
+    d.wait_act = fresh ? 1 : 0;
+    fresh = d.store != 0;
+    if (!d.store && st != dense.back()) ok = false;             // only the last layer may skip the store
+    sl.push_back(d);
+    for (const Pending& p : pend) {
+      if (p.producer != st->ord) continue;
+      const Layer& PL = net.layers[p.layer];
+      SplitLayerDesc v{};
+      v.n_out = PL.N;
+      v.park = 1;
+      push_maps(PL, p.seg, v);
+      v.wait_act = fresh ? 1 : 0;
+      if (!fresh || parked || v.kb != 4 || v.n_out != 256) ok = false;   // directly after a storing layer, one park at a time
+      fresh = false;
+      parked = true;
+      sl.push_back(v);
+    }
+  }
+  if (!ok || sl.empty() || net.w_view == nullptr) return 0;
+  if (dev_alloc(net, reinterpret_cast<void**>(&net.split_layers), sizeof(SplitLayerDesc) * sl.size())) return 1;
+  if (dev_alloc(net, reinterpret_cast<void**>(&net.split_wmaps), sizeof(CUtensorMap) * maps.size())) return 1;
+  CK(cudaMemcpyAsync(net.split_layers, sl.data(), sizeof(SplitLayerDesc) * sl.size(), cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(net.split_wmaps, maps.data(), sizeof(CUtensorMap) * maps.size(), cudaMemcpyHostToDevice, s));
+  CK(cudaStreamSynchronize(s));   // the host vectors go out of scope
+  net.split_n = static_cast<int>(sl.size());
+  return 0;
+}
+
 struct Workspace {
   float *z_c, *w_c, *z_f, *raw, *hp;
   __half *X0, *V, *T[3];
   __half* fscratch;    // fused coarse kernel: [num_sms * 128, 256] parked skip tensors
+  __half* X0lo;        // split-precision coarse kernel: low image of the point encoding [P_pad, 64]
+  float* ray_vec;      // ... per-ray view vector [groups, 128]
+  float* park;         // ... parked fp32 skip partial products, one [128 x 256] block per CTA
   int64_t P_pad;
   size_t total;
+};
+
+// Where the view directions of the point rows come from: one direction per `rows_per_group` consecutive rows.
+struct ViewSrc {
+  const float* dirs;
+  int stride;
+  int rows_per_group;
 };
 
 Workspace carve(void* base, int64_t n_chunk, int S_c, int S_f, int Wmax) {
@@ -271,6 +384,9 @@ Workspace carve(void* base, int64_t n_chunk, int S_c, int S_f, int Wmax) {
   w.V = reinterpret_cast<__half*>(b + take(sizeof(__half) * 64 * w.P_pad));
   for (int i = 0; i < 3; ++i) w.T[i] = reinterpret_cast<__half*>(b + take(sizeof(__half) * (size_t)Wmax * w.P_pad));
   w.fscratch = reinterpret_cast<__half*>(b + take(sizeof(__half) * 256 * 128 * kMaxSms));
+  w.X0lo = reinterpret_cast<__half*>(b + take(sizeof(__half) * 64 * w.P_pad));
+  w.ray_vec = reinterpret_cast<float*>(b + take(sizeof(float) * 128 * n_chunk));
+  w.park = reinterpret_cast<float*>(b + take(coarse_split_park_bytes(kMaxSms)));
   w.total = off;
   return w;
 }
@@ -283,14 +399,61 @@ int max_width(mofa_b200_ctx* c) {
 }
 
 // Runs the MLP program of `net` over the first P_pad rows of the workspace buffers.
+// True when `net` runs in the split-precision fused kernel for an inference pass (the caller must then have produced the
+// low image of the point encoding, ws.X0lo).
+bool use_split(const mofa_b200_ctx* c, const Net& net, uint32_t flags) {
+  return !(flags & MOFA_FLAG_GEMM_SIMT) && c->fused_coarse && c->split_coarse && net.split_n > 0 && c->num_sms <= kMaxSms;
+}
+
 int run_program(mofa_b200_ctx* c, Net& net, const Workspace& ws, int64_t P_rows, uint32_t flags, cudaStream_t s,
-                __half* const* act = nullptr) {
+                __half* const* act = nullptr, const ViewSrc* view = nullptr) {
   // act != nullptr: training mode — dense step k writes act[k] (kept for the backward pass) instead of the ping-pong buffers
   const int net_id = static_cast<int>(&net - c->nets);
   (void)net_id;
   const int64_t M = (P_rows + 127) / 128 * 128;
   auto src_ptr = [&](int id) -> __half* { return id == SRC_X0 ? ws.X0 : id == SRC_V ? ws.V : ws.T[id - SRC_T0]; };
   const bool tc = !(flags & MOFA_FLAG_GEMM_SIMT);
+  if (!act && view != nullptr && use_split(c, net, flags)) {
+    // whole network in one persistent CTA-pair kernel, fp16 hi+lo operands (fp32-class results)
+    const int64_t groups = (P_rows + view->rows_per_group - 1) / view->rows_per_group;
+    CK(launch_view_vec(view->dirs, view->stride, groups, net.w_view, net.W / 2, ws.ray_vec, s));
+    c->launches++;
+    SplitLaunch S;
+    memset(&S, 0, sizeof(S));
+    if (make_tmap_2d(c, &S.tmX0hi, ws.X0, (uint64_t)M, 64, 64, 128)) return 1;
+    if (make_tmap_2d(c, &S.tmX0lo, ws.X0lo, (uint64_t)M, 64, 64, 128)) return 1;
+    S.wmaps = net.split_wmaps;
+    S.layers = net.split_layers;
+    S.n_layers = net.split_n;
+    S.P_rows = P_rows;
+    S.w_alpha = net.w_alpha; S.b_alpha = net.b_alpha; S.w_rgb = net.w_rgb; S.b_rgb = net.b_rgb;
+    S.ray_vec = ws.ray_vec;
+    S.rows_per_group = view->rows_per_group;
+    S.park = ws.park;
+    S.raw = ws.raw;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (c->profiling) {
+      const size_t idx = c->recs.size() * 2;
+      while (c->ev.size() < idx + 2) {
+        cudaEvent_t e;
+        CK(cudaEventCreate(&e));
+        c->ev.push_back(e);
+      }
+      e0 = c->ev[idx];
+      e1 = c->ev[idx + 1];
+      CK(cudaEventRecord(e0, s));
+    }
+    CK(launch_coarse_split(S, c->num_sms, s));
+    if (c->profiling) {
+      double fl = 0.0;
+      for (const Step& st : net.program)
+        if (st.kind == 0) fl += 2.0 * (double)P_rows * (double)net.layers[st.layer].N * (double)net.layers[st.layer].in_ref;
+      CK(cudaEventRecord(e1, s));
+      c->recs.push_back({net_id, fl});
+    }
+    c->launches++;
+    return 0;
+  }
   if (tc && !act && c->fused_coarse && net.fused_n > 0 && c->num_sms <= kMaxSms) {
     // whole network in one persistent kernel (activations stay in shared memory)
     FusedLaunch F;
@@ -448,7 +611,10 @@ int mofa_b200_create(mofa_b200_ctx** out, int device) {
     c->pair_kernel = !(v && v[0] == '1');
     v = getenv("MOFA_B200_NO_FUSED_COARSE");
     c->fused_coarse = !(v && v[0] == '1');
+    v = getenv("MOFA_B200_COARSE_FP16");
+    c->split_coarse = !(v && v[0] == '1');
     if (e == cudaSuccess) e = mofa::coarse_fused_configure();
+    if (e == cudaSuccess) e = mofa::coarse_split_configure();
     if (e == cudaSuccess) e = mofa::wgrad_configure();
   }
   if (e != cudaSuccess) {
@@ -527,6 +693,10 @@ int mofa_b200_load_weights(mofa_b200_ctx* c, int net_id, int W, int D, const flo
         CK(launch_pack_weight(w, L.in_total, L.seg_c0[i], L.seg_kreal[i], L.K[i], L.N, L.w[i], s));
         CK(launch_pack_weight_t(w, L.in_total, L.seg_c0[i], L.seg_kreal[i], L.rows_t[i], L.N, L.wt[i], s));
         c->launches += 2;
+        if (L.wlo[i]) {
+          CK(launch_pack_weight_lo(w, L.in_total, L.seg_c0[i], L.seg_kreal[i], L.K[i], L.N, L.wlo[i], s));
+          c->launches++;
+        }
       }
       CK(cudaMemcpyAsync(L.bias_raw, b, sizeof(float) * L.N, cudaMemcpyDeviceToDevice, s));
       if (L.fold_n > 0)
@@ -537,6 +707,9 @@ int mofa_b200_load_weights(mofa_b200_ctx* c, int net_id, int W, int D, const flo
     CK(cudaMemcpyAsync(net.b_alpha, t[2 * nd + 1], sizeof(float), cudaMemcpyDeviceToDevice, s));
     CK(cudaMemcpyAsync(net.w_rgb, t[2 * nd + 2], sizeof(float) * 3 * (W / 2), cudaMemcpyDeviceToDevice, s));
     CK(cudaMemcpyAsync(net.b_rgb, t[2 * nd + 3], sizeof(float) * 3, cudaMemcpyDeviceToDevice, s));
+    if (net.w_view)   // view-direction columns of linear_view_xyBMuv (the last dense layer)
+      CK(cudaMemcpy2DAsync(net.w_view, sizeof(float) * kPeView, t[2 * (nd - 1)], sizeof(float) * (kPeView + W),
+                           sizeof(float) * kPeView, W / 2, cudaMemcpyDeviceToDevice, s));
     if (c->latents_set && fold_net(c, net, s)) return 1;
     return 0;
   }
@@ -629,6 +802,11 @@ int mofa_b200_load_weights(mofa_b200_ctx* c, int net_id, int W, int D, const flo
     sp.seg_c0[1] = kPeView; sp.seg_k[1] = W;       sp.seg_kpad[1] = W;
     if (build_layer(c, net, sp, w, b, s)) return 1;
     pb.dense(li++, SRC_V, pb.cur);
+    if (W == 256) {   // fp32 view-direction columns for the per-ray view vector of the split-precision kernel
+      if (dev_alloc(net, reinterpret_cast<void**>(&net.w_view), sizeof(float) * kPeView * (W / 2))) return 1;
+      CK(cudaMemcpy2DAsync(net.w_view, sizeof(float) * kPeView, w, sizeof(float) * (kPeView + W), sizeof(float) * kPeView,
+                           W / 2, cudaMemcpyDeviceToDevice, s));
+    }
   }
   // alpha_linear (W -> 1), rgb_linear (W/2 -> 3): fp32 copies for the SIMT heads
   next(w, b);
@@ -693,6 +871,7 @@ int mofa_b200_load_weights(mofa_b200_ctx* c, int net_id, int W, int D, const flo
       net.fused_n = static_cast<int>(fl.size());
     }
   }
+  if (W == 256 && build_split_table(c, net, s)) return 1;
   net.loaded = true;
   if (c->latents_set && fold_net(c, net, s)) return 1;
   return 0;
@@ -774,9 +953,14 @@ int mofa_b200_render_rays_fwd(mofa_b200_ctx* c, const mofa_b200_render_args* a, 
     // ---- coarse pass
     CK(launch_zvals_coarse(rays, a->ray_stride, n, S_c, lindisp, a->perturb, coff(a->t_rand, S_c), a->seed, r0,
                            ws.z_c, s));
-    CK(launch_encode_rays(rays, a->ray_stride, ws.z_c, n, S_c, kMultires, kMultiresViews, ws.X0, ws.V, s));
+    {
+      const bool sp = use_split(c, nc, a->flags);
+      CK(launch_encode_rays(rays, a->ray_stride, ws.z_c, n, S_c, kMultires, kMultiresViews, ws.X0, sp ? nullptr : ws.V, s,
+                            sp ? ws.X0lo : nullptr));
+    }
     c->launches += 2;
-    if (run_program(c, nc, ws, n * S_c, a->flags, s)) return 1;
+    const ViewSrc view_c{rays + 8, a->ray_stride, S_c};
+    if (run_program(c, nc, ws, n * S_c, a->flags, s, nullptr, &view_c)) return 1;
     float* o_rgb = fine ? off(a->rgb0, 3) : off(a->rgb, 3);
     float* o_disp = fine ? off(a->disp0, 1) : off(a->disp, 1);
     float* o_acc = fine ? off(a->acc0, 1) : off(a->acc, 1);
@@ -789,9 +973,14 @@ int mofa_b200_render_rays_fwd(mofa_b200_ctx* c, const mofa_b200_render_args* a, 
       const int det = (a->perturb == 0.0f) ? 1 : 0;
       CK(launch_sample_pdf_merge(ws.z_c, ws.w_c, coff(a->u, N_i), det, a->seed, r0, n, S_c, N_i, nullptr, ws.z_f,
                                  off(a->z_std, 1), s));
-      CK(launch_encode_rays(rays, a->ray_stride, ws.z_f, n, S_f, kMultires, kMultiresViews, ws.X0, ws.V, s));
+      {
+        const bool sp = use_split(c, nf, a->flags);
+        CK(launch_encode_rays(rays, a->ray_stride, ws.z_f, n, S_f, kMultires, kMultiresViews, ws.X0, sp ? nullptr : ws.V, s,
+                              sp ? ws.X0lo : nullptr));
+      }
       c->launches += 2;
-      if (run_program(c, nf, ws, n * S_f, a->flags, s)) return 1;
+      const ViewSrc view_f{rays + 8, a->ray_stride, S_f};
+      if (run_program(c, nf, ws, n * S_f, a->flags, s, nullptr, &view_f)) return 1;
       CK(launch_composite(ws.raw, ws.z_f, rays + 3, a->ray_stride, coff(a->noise_f, S_f), a->raw_noise_std,
                           a->seed + 0x9E3779B97F4A7C15ull, r0, n, S_f, white, off(a->rgb, 3), off(a->disp, 1),
                           off(a->acc, 1), a->weights ? off(a->weights, S_f) : nullptr, nullptr, s));
@@ -834,9 +1023,14 @@ int mofa_b200_run_network(mofa_b200_ctx* c, int net_id, const float* pts, const 
   Workspace ws = carve(wbase, n_pts, 1, 0, max_width(c));
   if (ws.total + slack > workspace_bytes)
     return fail("run_network: workspace too small (%zu < %zu)", workspace_bytes, ws.total + slack);
-  CK(launch_encode_points(pts, viewdirs, n_pts, kMultires, kMultiresViews, ws.X0, ws.V, s));
+  {
+    const bool sp = use_split(c, c->nets[net_id], flags);
+    CK(launch_encode_points(pts, viewdirs, n_pts, kMultires, kMultiresViews, ws.X0, sp ? nullptr : ws.V, s,
+                            sp ? ws.X0lo : nullptr));
+  }
   c->launches++;
-  if (run_program(c, c->nets[net_id], ws, n_pts, flags, s)) return 1;
+  const ViewSrc view{viewdirs, 3, 1};
+  if (run_program(c, c->nets[net_id], ws, n_pts, flags, s, nullptr, &view)) return 1;
   CK(launch_copy_f32(ws.raw, raw_out, n_pts * 4, s));
   c->launches++;
   return 0;

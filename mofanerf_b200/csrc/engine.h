@@ -53,11 +53,13 @@ cudaError_t launch_zvals_coarse(const float* rays, int stride, int64_t n, int S,
                                 const float* t_rand, uint64_t seed, int64_t ray_offset, float* z,
                                 cudaStream_t s);
 // points from rays + z  ->  fp16 PE rows X0 [P,64] (63 features + 0) and view PE rows V [P,64] (27 + 0)
+// X0lo (optional): fp16(value - float(X0)) — the low image for the split-precision coarse kernel; V may be nullptr
 cudaError_t launch_encode_rays(const float* rays, int stride, const float* z, int64_t n, int S,
-                               int multires, int multires_views, __half* X0, __half* V, cudaStream_t s);
+                               int multires, int multires_views, __half* X0, __half* V, cudaStream_t s,
+                               __half* X0lo = nullptr);
 // explicit points (run_network): pts [P,3], viewdirs [P,3]
 cudaError_t launch_encode_points(const float* pts, const float* viewdirs, int64_t P, int multires,
-                                 int multires_views, __half* X0, __half* V, cudaStream_t s);
+                                 int multires_views, __half* X0, __half* V, cudaStream_t s, __half* X0lo = nullptr);
 cudaError_t launch_embed_f32(const float* x, int64_t n, int multires, float* out, cudaStream_t s);
 // out[p*4 + off + j] = A[p,:]·Wh[j,:] + b[j]    (alpha_linear / rgb_linear)
 cudaError_t launch_head(const __half* A, int K, const float* Wh, const float* b, int nout, float* raw,
@@ -104,6 +106,41 @@ struct FusedLaunch {
 };
 cudaError_t launch_coarse_fused(const FusedLaunch& F, int num_sms, cudaStream_t stream);
 cudaError_t coarse_fused_configure();
+
+// ---- split-precision fused coarse-net kernel (coarse_split.cu) -----------------------------------
+struct SplitLayerDesc {
+  const float* bias;   // folded bias [n_out] fp32; nullptr for a virtual (park) layer
+  int n_out;           // 256, or 128 for the view layer
+  int kb;              // 64-wide K blocks of the resident activation this layer reads: 1 (point encoding) or 4
+  int map_hi, map_lo;  // weight tensor maps (fp16 hi / lo images, box = n_out/2 rows x 64 columns)
+  int wait_act;        // 1: first consumer of a freshly written activation (waits on the per-block barriers)
+  int store;           // write ReLU(out) as fp16 hi + lo images in place (the next layer's A operand)
+  int park;            // 1: virtual layer — raw fp32 accumulators go to the per-CTA scratch (skip partial product)
+  int add_park;        // 1: add the parked partial product (the skip layer)
+  int add_ray;         // 1: add the per-ray view vector (view layer)
+  int head;            // 0 none, 1 alpha_linear, 2 rgb_linear (computed in the epilogue)
+};
+struct SplitLaunch {
+  CUtensorMap tmX0hi, tmX0lo;      // [P_pad, 64] fp16 point encodings (hi, lo), box {64, 128}
+  const CUtensorMap* wmaps;        // device array
+  const SplitLayerDesc* layers;    // device array
+  int n_layers;
+  int64_t P_rows;
+  const float *w_alpha, *b_alpha, *w_rgb, *b_rgb;
+  const float* ray_vec;            // [groups, 128] fp32 (launch_view_vec)
+  int rows_per_group;              // consecutive point rows that share a view direction (samples per ray)
+  float* park;                     // coarse_split_park_bytes()
+  float* raw;
+};
+cudaError_t launch_coarse_split(const SplitLaunch& S, int num_sms, cudaStream_t stream);
+cudaError_t coarse_split_configure();
+size_t coarse_split_park_bytes(int num_sms);
+// out[g, c] = sum_k Wv[c, k] * PE_4(dirs[g])[k], Wv [n_out, 27] fp32
+cudaError_t launch_view_vec(const float* dirs, int stride, int64_t n, const float* Wv, int n_out, float* out,
+                            cudaStream_t s);
+// dst = fp16(w - float(fp16(w))): the low image of the split-precision weights (same layout as launch_pack_weight)
+cudaError_t launch_pack_weight_lo(const float* src, int ld, int c0, int k, int kpad, int nrows, __half* dst,
+                                  cudaStream_t s);
 
 // ---- backward pass (backward.cu) ----------------------------------------------------------------
 cudaError_t launch_composite_bwd(const float* raw, const float* z, const float* rays, int stride, const float* noise,

@@ -97,38 +97,55 @@ cudaError_t launch_zvals_coarse(const float* rays, int stride, int64_t n, int S,
 // positional encoding
 // ------------------------------------------------------------------------------------------------
 // Writes one 64-half row: [x, y, z, sin(2^0 p), cos(2^0 p), ..., sin(2^(L-1) p), cos(2^(L-1) p), 0...]
+// row_lo (optional): the fp16 remainder value - float(fp16(value)) of every feature (split-precision coarse kernel)
 template <int L>
-__device__ __forceinline__ void pe_row_f16(float x, float y, float z, __half* __restrict__ row) {
+__device__ __forceinline__ void pe_row_f16(float x, float y, float z, __half* __restrict__ row,
+                                           __half* __restrict__ row_lo = nullptr) {
   static_assert(3 + 6 * L <= 64, "PE row must fit one 64-wide K block");
   __align__(16) __half h[64];
+  __align__(16) __half lo[64];
 #pragma unroll
-  for (int i = 0; i < 64; ++i) h[i] = __float2half_rn(0.0f);
-  h[0] = __float2half_rn(x);
-  h[1] = __float2half_rn(y);
-  h[2] = __float2half_rn(z);
+  for (int i = 0; i < 64; ++i) {
+    h[i] = __float2half_rn(0.0f);
+    lo[i] = __float2half_rn(0.0f);
+  }
+  auto put = [&](int i, float v) {
+    h[i] = __float2half_rn(v);
+    lo[i] = __float2half_rn(v - __half2float(h[i]));
+  };
+  put(0, x);
+  put(1, y);
+  put(2, z);
 #pragma unroll
   for (int f = 0; f < L; ++f) {
     const float fr = static_cast<float>(1 << f);
     float s, c;
     sincosf(x * fr, &s, &c);
-    h[3 + 6 * f + 0] = __float2half_rn(s);
-    h[3 + 6 * f + 3] = __float2half_rn(c);
+    put(3 + 6 * f + 0, s);
+    put(3 + 6 * f + 3, c);
     sincosf(y * fr, &s, &c);
-    h[3 + 6 * f + 1] = __float2half_rn(s);
-    h[3 + 6 * f + 4] = __float2half_rn(c);
+    put(3 + 6 * f + 1, s);
+    put(3 + 6 * f + 4, c);
     sincosf(z * fr, &s, &c);
-    h[3 + 6 * f + 2] = __float2half_rn(s);
-    h[3 + 6 * f + 5] = __float2half_rn(c);
+    put(3 + 6 * f + 2, s);
+    put(3 + 6 * f + 5, c);
   }
   uint4* dst = reinterpret_cast<uint4*>(row);
   const uint4* src = reinterpret_cast<const uint4*>(h);
 #pragma unroll
   for (int i = 0; i < 8; ++i) dst[i] = src[i];
+  if (row_lo != nullptr) {
+    uint4* dl = reinterpret_cast<uint4*>(row_lo);
+    const uint4* sl = reinterpret_cast<const uint4*>(lo);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dl[i] = sl[i];
+  }
 }
 
 template <int LX, int LV>
 __global__ void encode_rays_kernel(const float* __restrict__ rays, int stride, const float* __restrict__ z,
-                                   int64_t n, int S, __half* __restrict__ X0, __half* __restrict__ V) {
+                                   int64_t n, int S, __half* __restrict__ X0, __half* __restrict__ V,
+                                   __half* __restrict__ X0lo) {
   const int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (p >= n * S) return;
   const int64_t r = p / S;
@@ -138,33 +155,33 @@ __global__ void encode_rays_kernel(const float* __restrict__ rays, int stride, c
   const float px = __fadd_rn(ray[0], __fmul_rn(ray[3], zi));
   const float py = __fadd_rn(ray[1], __fmul_rn(ray[4], zi));
   const float pz = __fadd_rn(ray[2], __fmul_rn(ray[5], zi));
-  pe_row_f16<LX>(px, py, pz, X0 + p * 64);
-  pe_row_f16<LV>(ray[8], ray[9], ray[10], V + p * 64);
+  pe_row_f16<LX>(px, py, pz, X0 + p * 64, X0lo ? X0lo + p * 64 : nullptr);
+  if (V != nullptr) pe_row_f16<LV>(ray[8], ray[9], ray[10], V + p * 64);
 }
 
 template <int LX, int LV>
 __global__ void encode_points_kernel(const float* __restrict__ pts, const float* __restrict__ vd, int64_t P,
-                                     __half* __restrict__ X0, __half* __restrict__ V) {
+                                     __half* __restrict__ X0, __half* __restrict__ V, __half* __restrict__ X0lo) {
   const int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (p >= P) return;
-  pe_row_f16<LX>(pts[p * 3 + 0], pts[p * 3 + 1], pts[p * 3 + 2], X0 + p * 64);
-  pe_row_f16<LV>(vd[p * 3 + 0], vd[p * 3 + 1], vd[p * 3 + 2], V + p * 64);
+  pe_row_f16<LX>(pts[p * 3 + 0], pts[p * 3 + 1], pts[p * 3 + 2], X0 + p * 64, X0lo ? X0lo + p * 64 : nullptr);
+  if (V != nullptr) pe_row_f16<LV>(vd[p * 3 + 0], vd[p * 3 + 1], vd[p * 3 + 2], V + p * 64);
 }
 
 cudaError_t launch_encode_rays(const float* rays, int stride, const float* z, int64_t n, int S, int multires,
-                               int multires_views, __half* X0, __half* V, cudaStream_t s) {
+                               int multires_views, __half* X0, __half* V, cudaStream_t s, __half* X0lo) {
   if (multires != 10 || multires_views != 4) return cudaErrorInvalidValue;
   const int64_t tot = n * S;
   if (tot == 0) return cudaSuccess;
-  encode_rays_kernel<10, 4><<<static_cast<unsigned>((tot + 127) / 128), 128, 0, s>>>(rays, stride, z, n, S, X0, V);
+  encode_rays_kernel<10, 4><<<static_cast<unsigned>((tot + 127) / 128), 128, 0, s>>>(rays, stride, z, n, S, X0, V, X0lo);
   return cudaGetLastError();
 }
 
 cudaError_t launch_encode_points(const float* pts, const float* viewdirs, int64_t P, int multires,
-                                 int multires_views, __half* X0, __half* V, cudaStream_t s) {
+                                 int multires_views, __half* X0, __half* V, cudaStream_t s, __half* X0lo) {
   if (multires != 10 || multires_views != 4) return cudaErrorInvalidValue;
   if (P == 0) return cudaSuccess;
-  encode_points_kernel<10, 4><<<static_cast<unsigned>((P + 127) / 128), 128, 0, s>>>(pts, viewdirs, P, X0, V);
+  encode_points_kernel<10, 4><<<static_cast<unsigned>((P + 127) / 128), 128, 0, s>>>(pts, viewdirs, P, X0, V, X0lo);
   return cudaGetLastError();
 }
 
@@ -494,6 +511,22 @@ cudaError_t launch_pack_weight(const float* src, int ld, int c0, int k, int kpad
                                cudaStream_t s) {
   const int64_t tot = static_cast<int64_t>(nrows) * kpad;
   pack_weight_kernel<<<static_cast<unsigned>((tot + 255) / 256), 256, 0, s>>>(src, ld, c0, k, kpad, nrows, dst);
+  return cudaGetLastError();
+}
+
+__global__ void pack_weight_lo_kernel(const float* __restrict__ src, int ld, int c0, int k, int kpad, int nrows,
+                                      __half* __restrict__ dst) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<int64_t>(nrows) * kpad) return;
+  const int r = static_cast<int>(i / kpad), c = static_cast<int>(i % kpad);
+  const float w = c < k ? src[static_cast<int64_t>(r) * ld + c0 + c] : 0.0f;
+  dst[i] = __float2half_rn(w - __half2float(__float2half_rn(w)));
+}
+
+cudaError_t launch_pack_weight_lo(const float* src, int ld, int c0, int k, int kpad, int nrows, __half* dst,
+                                  cudaStream_t s) {
+  const int64_t tot = static_cast<int64_t>(nrows) * kpad;
+  pack_weight_lo_kernel<<<static_cast<unsigned>((tot + 255) / 256), 256, 0, s>>>(src, ld, c0, k, kpad, nrows, dst);
   return cudaGetLastError();
 }
 

@@ -145,12 +145,18 @@ def test_frame_crop_config5_identities_through_render(name):
     c, f, s, r = build_reference_like(int(meta["seed"]))
     r = r.to(DEV)
     uv = torch.rand(512, 512, 3, generator=torch.Generator().manual_seed(int(inp["uv_seed"])))
+    # the fixture's texture code comes from the reference's fp32 CPU convolutions; PyTorch's default on GPU lets cuDNN
+    # use TF32 for convolutions (4e-4 on the code, measured) — the engine is not involved in that step, so pin it to fp32
+    # here to feed both sides the same latent ("identical rays and latents")
+    tf32_was = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
     with torch.no_grad():
         out = r.render(int(meta["H"]), int(meta["W"]), inp["K"].numpy(), chunk=1 << 20,
                        rays=(inp["rays_o"].to(DEV), inp["rays_d"].to(DEV)), shapeCodes=inp["shape"].to(DEV),
                        uvMap=uv.to(DEV), expType=int(inp["exp_slot"]), **_crop_kwargs(meta, c, f))
         tex = r.decoding_texCodes.reshape(-1).cpu()
     torch.cuda.synchronize()
+    torch.backends.cudnn.allow_tf32 = tf32_was
     d_tex = (tex - inp["tex"]).abs().max().item()
     parity_log.record(name, tex_code_max=d_tex)
     assert d_tex <= 1e-4, f"texture encoder (cuDNN) vs reference (CPU): {d_tex:.2e}"
@@ -166,7 +172,10 @@ def test_simt_and_tensor_core_paths_agree():
     d0 = (a["rgb0"] - b["rgb0"]).abs().max().item()
     d = (a["rgb_map"] - b["rgb_map"]).abs().max().item()
     print(f"[parity] tcgen05 vs SIMT: rgb0 {d0:.2e} rgb {d:.2e}")
-    assert d0 <= 1e-3 and d <= 6e-2, f"tcgen05 vs SIMT dense kernels disagree: coarse {d0:.3e} final {d:.3e}"
+    parity_log.record("small_w256[simt vs tcgen05]", rgb0_max=d0, rgb_map_max=d)
+    # the default coarse path is split precision (fp32-class), the SIMT verification path single fp16: they differ by the
+    # fp16 chain's own error on the coarse maps (~1e-3)
+    assert d0 <= 2e-3 and d <= 6e-2, f"tcgen05 vs SIMT dense kernels disagree: coarse {d0:.3e} final {d:.3e}"
 
 
 @pytest.mark.parametrize("name", ["small_w256", "full_w1024", "perturb_pytest"])
@@ -260,10 +269,49 @@ def test_run_network_matches_nerf_forward():
     assert d.max().item() <= 2e-2 * max(1.0, scale)
 
 
+def test_split_precision_coarse_kernel_is_fp32_class():
+    """The coarse net (W = 256) runs on the tensor cores in split precision (fp16 hi + lo operands, three products per
+    layer, coarse_split.cu): its per-point outputs must sit at the fp32 noise floor of the reference itself (the oracle
+    changes by 2.5e-5 between netchunk blockings) — not at the 1e-2 of a single-fp16 chain.  Also pins the
+    single-fp16 fused kernel of round 1 (MOFA_B200_COARSE_FP16=1, a separate engine) on the same points."""
+    import os
+    from mofanerf_b200.engine import Engine
+    meta, inp, _ = load_case("full_w1024")
+    c, f, s = build_case_nets(meta)
+    g = torch.Generator().manual_seed(17)
+    n, S = 37, 64                       # 2368 points: not a multiple of the 256-row pair tile
+    rays = O.make_ray_batch(inp["rays_o"][:n], inp["rays_d"][:n], 8.0, 26.0)
+    z = torch.sort(8.0 + 18.0 * torch.rand(n, S, generator=g), -1)[0]
+    pts = rays[:, None, 0:3] + rays[:, None, 3:6] * z[..., None]
+    em = O.expression_mod(s, inp["shape"], inp["exp"])
+    with torch.no_grad():
+        ref = O.run_network(pts, rays[:, 8:11], c, inp["shape"], em, inp["tex"])
+    scale = max(1.0, ref.abs().max().item())
+    res = {}
+    for mode in ("split", "fp16"):
+        if mode == "fp16":
+            os.environ["MOFA_B200_COARSE_FP16"] = "1"
+        try:
+            eng = Engine(DEV)
+        finally:
+            os.environ.pop("MOFA_B200_COARSE_FP16", None)
+        eng.load_network(0, c.to(DEV))
+        eng.set_latents(inp["shape"], em, inp["tex"])
+        out = eng.run_network(0, pts.to(DEV), rays[:, None, 8:11].to(DEV)).cpu()
+        torch.cuda.synchronize()
+        eng.close()
+        res[mode] = (out - ref).abs().max().item()
+    print(f"[parity] coarse raw vs fp32 oracle: split {res['split']:.3e}, single fp16 {res['fp16']:.3e} (|ref|max {scale:.2f})")
+    parity_log.record("coarse net raw[split vs fp16]", split_max=res["split"], fp16_max=res["fp16"], raw_refmax=scale)
+    assert res["split"] <= 2e-4 * scale, f"split-precision coarse kernel: {res['split']:.3e}"
+    assert res["fp16"] <= 2e-2 * scale, f"single-fp16 fused coarse kernel: {res['fp16']:.3e}"
+    assert res["split"] < 0.1 * res["fp16"]
+
+
 def test_training_mode_forward_equals_inference_forward():
     """With grad-requiring inputs the renderer switches to the activation-keeping forward (fitting).  It runs the
-    per-layer kernels where inference runs the fused coarse kernel (different fp32 summation order in the heads), so the
-    maps agree to rounding, not bit for bit: coarse maps 5e-4, final maps 5e-3 (resampling feedback)."""
+    per-layer single-fp16 kernels where inference runs the split-precision fused coarse kernel, so the maps agree to the
+    fp16 chain's error, not bit for bit: coarse maps 2e-3, final maps 2e-2 (resampling feedback)."""
     from mofanerf_b200 import B200Renderer
     meta, inp, _ = load_case("small_w256")
     c, f, s = build_case_nets(meta)
@@ -276,5 +324,5 @@ def test_training_mode_forward_equals_inference_forward():
         a = r.render_fitting(4, 4, None, shapeCodes=inp["shape"].to(DEV), **args)
     b = r.render_fitting(4, 4, None, shapeCodes=inp["shape"].to(DEV).requires_grad_(True), **args)
     assert b[0].requires_grad and b[0].grad_fn is not None
-    assert (a[3]["rgb0"] - b[3]["rgb0"].detach()).abs().max().item() <= 5e-4
-    assert (a[0] - b[0].detach()).abs().max().item() <= 5e-3 and (a[2] - b[2].detach()).abs().max().item() <= 5e-3
+    assert (a[3]["rgb0"] - b[3]["rgb0"].detach()).abs().max().item() <= 2e-3
+    assert (a[0] - b[0].detach()).abs().max().item() <= 2e-2 and (a[2] - b[2].detach()).abs().max().item() <= 2e-2
