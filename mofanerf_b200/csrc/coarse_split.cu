@@ -17,7 +17,7 @@
 //     CTA loading its half of the N rows (cta_group::2: the pair's tensor cores read both halves, so L2->SM bytes per
 //     point are those of the single-precision kernel although the weights are twice as large);
 //   * accumulators double-buffer in TMEM, so layer l+1's MMAs on K block j start when layer l's epilogue has produced
-//     column block j (per-block mbarriers; the peer CTA arrives remotely with release.cluster semantics);
+//     column block j (per-block mbarriers; the peer CTA's warps arrive remotely on the leader's barriers);
 //   * no second A operand anywhere: the skip layers' partial product  W[:, x_in] · x_in  is computed while x_in is
 //     still the resident activation (a "virtual" layer right after its producer), parked as fp32 in a per-CTA scratch
 //     (L2-resident, coalesced) and added in the skip layer's epilogue; the view-direction columns of the view layer are
@@ -173,7 +173,7 @@ coarse_split_kernel(const __grid_constant__ CUtensorMap tmX0hi, const __grid_con
                 x0_ph ^= 1u;
               }
             } else if (d.wait_act) {
-              mbar_wait_cluster(act_ready0 + 8 * kb, ready_ph);   // both CTAs' epilogues have written K block kb
+              mbar_wait(act_ready0 + 8 * kb, ready_ph);           // both CTAs' epilogues have written K block kb
             }
             const uint64_t a_hi = umma_desc_sw128_kmajor(act_hi + kb * kAKb);
             const uint64_t a_lo = umma_desc_sw128_kmajor(act_lo + kb * kAKb);
@@ -242,86 +242,107 @@ coarse_split_kernel(const __grid_constant__ CUtensorMap tmX0hi, const __grid_con
         const float* hw = d.head == 1 ? w_alpha : w_rgb;
         const int hn = d.head == 1 ? 1 : (d.head == 2 ? 3 : 0);
         const int ncb = d.n_out >> 6, half_cb = ncb >> 1;
-#pragma unroll 1
-        for (int cb = grp * half_cb; cb < (grp + 1) * half_cb; ++cb) {
+        // This warp's 32-column chunks of the tile: chunk q covers columns [(grp * half_cb) * 64 + q * 32, +32).  The
+        // additive terms of chunk q + 1 (bias, parked skip partial or per-ray view vector) are fetched while chunk q is
+        // being processed, and chunk q's own TMEM load is issued before anything else, so the only exposed latency per
+        // chunk is the TMEM load itself (with every fetch after the TMEM wait the epilogue was 75 % stalled on them).
+        const int nchunk = 2 * half_cb;
+        const int col0 = grp * half_cb * 64;
+        auto fetch_add = [&](int ncol, float4 (&ad)[8]) {
+          if (d.park) return;
+          const float4* bias4 = reinterpret_cast<const float4*>(d.bias + ncol);
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            uint32_t v[32];
-            tmem_ld_32x32b_x32(tmem_base + lane_base + acc * 256 + cb * 64 + h * 32, v);
-            const int ncol = cb * 64 + h * 32;
-            // the parked skip partial / per-ray view vector of these 32 columns: fetched while the TMEM load is in flight
-            float4 ad[8];
-            if (d.add_park) {
+          for (int i = 0; i < 8; ++i) ad[i] = __ldg(bias4 + i);
+          if (d.add_park) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) ad[i] = park4[(ncol / 4 + i) * 128 + row];
-            } else if (d.add_ray) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) ad[i] = __ldg(rv4 + ncol / 4 + i);
-            } else {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) ad[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = 0; i < 8; ++i) {
+              const float4 p = park4[(ncol / 4 + i) * 128 + row];
+              ad[i].x += p.x; ad[i].y += p.y; ad[i].z += p.z; ad[i].w += p.w;
             }
-            tmem_ld_wait();
-            if (d.park) {            // virtual layer: raw accumulators to the scratch, nothing else
+          } else if (d.add_ray) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i)
-                park4[(ncol / 4 + i) * 128 + row] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
-                                                                __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
-              continue;
-            }
-            const float4* bias4 = reinterpret_cast<const float4*>(d.bias + ncol);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float4 b0 = __ldg(bias4 + 2 * j), b1 = __ldg(bias4 + 2 * j + 1);
-              const float4 a0 = ad[2 * j], a1 = ad[2 * j + 1];
-              float f[8];
-              f[0] = fmaxf(__uint_as_float(v[j * 8 + 0]) + a0.x + b0.x, 0.f);
-              f[1] = fmaxf(__uint_as_float(v[j * 8 + 1]) + a0.y + b0.y, 0.f);
-              f[2] = fmaxf(__uint_as_float(v[j * 8 + 2]) + a0.z + b0.z, 0.f);
-              f[3] = fmaxf(__uint_as_float(v[j * 8 + 3]) + a0.w + b0.w, 0.f);
-              f[4] = fmaxf(__uint_as_float(v[j * 8 + 4]) + a1.x + b1.x, 0.f);
-              f[5] = fmaxf(__uint_as_float(v[j * 8 + 5]) + a1.y + b1.y, 0.f);
-              f[6] = fmaxf(__uint_as_float(v[j * 8 + 6]) + a1.z + b1.z, 0.f);
-              f[7] = fmaxf(__uint_as_float(v[j * 8 + 7]) + a1.w + b1.w, 0.f);
-              if (hn > 0) {
-#pragma unroll
-                for (int q = 0; q < 3; ++q) {
-                  if (q >= hn) break;
-                  const float4* w4 = reinterpret_cast<const float4*>(hw + q * d.n_out + ncol) + 2 * j;
-                  const float4 w0 = __ldg(w4), w1 = __ldg(w4 + 1);
-                  hacc[q] += f[0] * w0.x + f[1] * w0.y + f[2] * w0.z + f[3] * w0.w + f[4] * w1.x + f[5] * w1.y +
-                             f[6] * w1.z + f[7] * w1.w;
-                }
-              }
-              if (d.store) {
-                // hi = fp16(x) (saturated at the fp16 maximum), lo = fp16(x - hi): the pair carries ~22 mantissa bits
-                uint32_t ph[4], pl[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(ph[e]) : "f"(f[2 * e + 1]), "f"(f[2 * e]));
-                  asm("min.f16x2 %0, %0, %1;" : "+r"(ph[e]) : "r"(0x7bff7bffu));
-                  const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&ph[e]));
-                  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(pl[e]) : "f"(f[2 * e + 1] - hf.y), "f"(f[2 * e] - hf.x));
-                  asm("min.f16x2 %0, %0, %1;" : "+r"(pl[e]) : "r"(0x7bff7bffu));
-                }
-                const int chunk = h * 4 + j;
-                const uint32_t off = cb * kAKb + row * 128 + ((chunk ^ (row & 7)) << 4);
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(act_hi + off), "r"(ph[0]), "r"(ph[1]),
-                             "r"(ph[2]), "r"(ph[3])
-                             : "memory");
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(act_lo + off), "r"(pl[0]), "r"(pl[1]),
-                             "r"(pl[2]), "r"(pl[3])
-                             : "memory");
-              }
+            for (int i = 0; i < 8; ++i) {
+              const float4 p = __ldg(rv4 + ncol / 4 + i);
+              ad[i].x += p.x; ad[i].y += p.y; ad[i].z += p.z; ad[i].w += p.w;
             }
           }
-          if (d.store) {                  // K block cb of the next layer's A operand is complete for this warp's rows
+        };
+        float4 ad[8], adn[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ad[i] = adn[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        fetch_add(col0, ad);
+#pragma unroll 1
+        for (int q = 0; q < nchunk; ++q) {
+          const int ncol = col0 + q * 32;
+          const int cb = ncol >> 6, h = (ncol >> 5) & 1;
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tmem_base + lane_base + acc * 256 + ncol, v);
+          if (q + 1 < nchunk) fetch_add(ncol + 32, adn);
+          tmem_ld_wait();
+          if (d.park) {            // virtual layer: raw accumulators to the scratch, nothing else
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              park4[(ncol / 4 + i) * 128 + row] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                                              __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+            continue;
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 a0 = ad[2 * j], a1 = ad[2 * j + 1];
+            float f[8];
+            f[0] = fmaxf(__uint_as_float(v[j * 8 + 0]) + a0.x, 0.f);
+            f[1] = fmaxf(__uint_as_float(v[j * 8 + 1]) + a0.y, 0.f);
+            f[2] = fmaxf(__uint_as_float(v[j * 8 + 2]) + a0.z, 0.f);
+            f[3] = fmaxf(__uint_as_float(v[j * 8 + 3]) + a0.w, 0.f);
+            f[4] = fmaxf(__uint_as_float(v[j * 8 + 4]) + a1.x, 0.f);
+            f[5] = fmaxf(__uint_as_float(v[j * 8 + 5]) + a1.y, 0.f);
+            f[6] = fmaxf(__uint_as_float(v[j * 8 + 6]) + a1.z, 0.f);
+            f[7] = fmaxf(__uint_as_float(v[j * 8 + 7]) + a1.w, 0.f);
+            if (hn > 0) {
+#pragma unroll
+              for (int qq = 0; qq < 3; ++qq) {
+                if (qq >= hn) break;
+                const float4* w4 = reinterpret_cast<const float4*>(hw + qq * d.n_out + ncol) + 2 * j;
+                const float4 w0 = __ldg(w4), w1 = __ldg(w4 + 1);
+                hacc[qq] += f[0] * w0.x + f[1] * w0.y + f[2] * w0.z + f[3] * w0.w + f[4] * w1.x + f[5] * w1.y +
+                            f[6] * w1.z + f[7] * w1.w;
+              }
+            }
+            if (d.store) {
+              // hi = fp16(x) (saturated at the fp16 maximum), lo = fp16(x - hi): the pair carries ~22 mantissa bits
+              uint32_t ph[4], pl[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(ph[e]) : "f"(f[2 * e + 1]), "f"(f[2 * e]));
+                asm("min.f16x2 %0, %0, %1;" : "+r"(ph[e]) : "r"(0x7bff7bffu));
+                const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&ph[e]));
+                asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(pl[e]) : "f"(f[2 * e + 1] - hf.y), "f"(f[2 * e] - hf.x));
+                asm("min.f16x2 %0, %0, %1;" : "+r"(pl[e]) : "r"(0x7bff7bffu));
+              }
+              const int chunk = h * 4 + j;
+              const uint32_t off = cb * kAKb + row * 128 + ((chunk ^ (row & 7)) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(act_hi + off), "r"(ph[0]), "r"(ph[1]),
+                           "r"(ph[2]), "r"(ph[3])
+                           : "memory");
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(act_lo + off), "r"(pl[0]), "r"(pl[1]),
+                           "r"(pl[2]), "r"(pl[3])
+                           : "memory");
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) ad[i] = adn[i];
+          if (d.store && h == 1) {        // K block cb of the next layer's A operand is complete for this warp's rows
             fence_proxy_async_smem();
             tc_fence_before();
             __syncwarp();
+            // The peer CTA arrives on the leader's barrier with the default (CTA-scope release) semantics, as the pair
+            // kernel's accumulator hand-off does: the data are this thread's own st.shared, made visible to the async
+            // proxy by the fence above, and the MMA that reads them is issued only after the leader has seen the arrive.
+            // (The explicit .release.cluster form compiled to MEMBAR.ALL.GPU + CCTL.IVALL + ERRBAR: 20 % of the peer
+            // epilogue's samples, and the L1 invalidation made every bias / park fetch that followed miss.)
             if (lane == 0) {
               if (leader) mbar_arrive(act_ready0 + 8 * cb);
-              else mbar_arrive_cluster_release(mapa_u32(act_ready0 + 8 * cb, 0));
+              else mbar_arrive_cluster(mapa_u32(act_ready0 + 8 * cb, 0));
             }
           }
         }

@@ -2,19 +2,21 @@
   (1) the fixtures produced by the unmodified reference (tests/golden/*.npz) and
   (2) the oracle run on the same inputs.
 
-Stated tolerance (north_star: "within a stated fp32 tolerance"): the dense layers use fp16 operands with
-fp32 accumulation (SURVEY.md §7 'Precision'), every other stage is fp32.  For rendered maps in [0,1]:
-  * stage-wise, on identical sample points (test_teacher_forced_stages): per-point network outputs
-    within 2e-2 * max(1, |raw|max), composited rgb within 4e-3 — this is the precision of the fp16 dense
-    chain itself;
-  * end to end: max |Δrgb| <= 6e-2, mean |Δrgb| <= 3e-3, PSNR(engine, reference) >= 40 dB, acc within
-    3e-2; disparity where acc > 1e-3 within 5e-2 relative; NaN positions coincide where the reference's
-    acc is exactly 0.  The end-to-end bound is looser than the stage-wise one because hierarchical
-    resampling feeds the coarse pass's weights back into the sample *positions*, and a random-init
-    field with 2^9 positional frequencies is not smooth: a 1e-4 change in coarse weights moves a few fine
-    samples by ~1e-3 and the colour there by ~1e-2 (the reference shows the same sensitivity between its own
-    CPU and CUDA runs).  The SIMT verification kernel (same fp16 operands, different accumulation order)
-    is held to the same bounds and must agree with the tensor-core kernel to 1e-3 on the coarse maps.
+Stated tolerance (north_star: "within a stated fp32 tolerance"; SURVEY.md §7 / BASELINE.md §4.4 ask for
+max |Δrgb| <= 3e-2, mean <= 3e-3, PSNR >= 45 dB): the coarse net runs in split precision (fp16 hi+lo operands, three
+tensor-core products per layer, fp32 accumulation: fp32-class), the fine net's dense layers use single fp16 operands
+with fp32 accumulation, every other stage is fp32.  For rendered maps in [0,1]:
+  * coarse maps (rgb0 / acc0): max <= 5e-5 (measured 2e-6 .. 5e-6: the reference's own fp32 noise floor);
+  * stage-wise, on identical sample points (test_teacher_forced_stages): per-point fine-net outputs within
+    2e-2 * max(1, |raw|max), composited rgb within 2e-3 (measured 5e-4) — the precision of the fp16 dense chain;
+  * end to end: max |Δrgb| <= 3e-2, mean |Δrgb| <= 1e-3, PSNR(engine, reference) >= 50 dB (measured over all fixtures:
+    max <= 1.5e-2, mean <= 2.9e-4, PSNR 58 .. 112 dB; table in profiles/parity_r02.json), acc within 3e-2; disparity
+    where acc > 1e-3 within 5e-2 relative; NaN positions coincide where the reference's acc is exactly 0.  The per-ray
+    maximum is looser than the mean because inverse-CDF resampling is discontinuous: an fp32-rounding-level change of a
+    coarse weight can move one fine sample across a bin of a random-init field with 2^9 positional frequencies (the
+    reference shows the same sensitivity between its own CPU and CUDA runs).  The SIMT verification kernel (single fp16
+    operands, different accumulation order) is held to the same end-to-end bounds and agrees with the default path to
+    2e-3 on the coarse maps (its own fp16 error).
 Ray order is bit-exact by construction and tested (output row i <-> input ray i).
 """
 import numpy as np
@@ -55,7 +57,8 @@ def engine_render(meta, inp, nets, gemm_simt=False, chunk=1024 * 32, want_aux=Fa
     return {k: v.float().cpu() for k, v in out.items()}
 
 
-def check_maps(name, got, ref, max_rgb=6e-2, mean_rgb=3e-3, min_psnr=40.0, max_acc=3e-2, disp_min_acc=1e-3):
+def check_maps(name, got, ref, max_rgb=3e-2, mean_rgb=1e-3, min_psnr=50.0, max_acc=3e-2, disp_min_acc=1e-3,
+               max_rgb0=5e-5):
     msgs = []
     for k in ("rgb_map", "rgb0"):   # measured numbers go to profiles/parity_r02.json before anything is asserted
         if k in ref:
@@ -71,6 +74,8 @@ def check_maps(name, got, ref, max_rgb=6e-2, mean_rgb=3e-3, min_psnr=40.0, max_a
             ps = O.psnr(got[k], ref[k])
             msgs.append(f"{k}: max {d.max().item():.2e} mean {d.mean().item():.2e} psnr {ps:.1f}")
             assert d.max().item() <= max_rgb and d.mean().item() <= mean_rgb and ps >= min_psnr, f"{name} {msgs[-1]}"
+            if k == "rgb0" and max_rgb0 is not None:      # the coarse pass is fp32-class
+                assert d.max().item() <= max_rgb0, f"{name} {msgs[-1]}"
     for k in ("acc_map", "acc0"):
         if k in ref:
             d = (got[k] - ref[k]).abs().max().item()
@@ -99,14 +104,7 @@ def check_maps(name, got, ref, max_rgb=6e-2, mean_rgb=3e-3, min_psnr=40.0, max_a
 def test_against_reference_fixtures(name):
     meta, inp, gold = load_case(name)
     got = engine_render(meta, inp, build_case_nets(meta))
-    if name == "perturb_pytest":
-        # worst-conditioned case by construction: random (not stratified-sorted) u in sample_pdf, unit-scale
-        # sigma noise on a nearly empty field; PSNR and the mean stay at the common bound, the per-ray maxima
-        # are allowed 1e-1 (see test_teacher_forced_stages[perturb_pytest] for the same case without the
-        # resampling feedback: 4e-3).
-        check_maps(name, got, gold, max_rgb=1e-1, max_acc=1e-1, disp_min_acc=0.3)   # disp = acc/depth: ill-conditioned on faint rays
-    else:
-        check_maps(name, got, gold)
+    check_maps(name, got, gold)     # one bound for every fixture, the seeded-random (pytest=True) case included
 
 
 def _crop_kwargs(meta, c, f):
@@ -168,7 +166,7 @@ def test_simt_and_tensor_core_paths_agree():
     nets = build_case_nets(meta)
     a = engine_render(meta, inp, nets, gemm_simt=False)
     b = engine_render(meta, inp, nets, gemm_simt=True)
-    check_maps("small_w256[simt]", b, gold)
+    check_maps("small_w256[simt]", b, gold, max_rgb0=2e-3)    # single fp16 on the coarse pass as well
     d0 = (a["rgb0"] - b["rgb0"]).abs().max().item()
     d = (a["rgb_map"] - b["rgb_map"]).abs().max().item()
     print(f"[parity] tcgen05 vs SIMT: rgb0 {d0:.2e} rgb {d:.2e}")
@@ -217,7 +215,7 @@ def test_teacher_forced_stages(name):
     dw = (w_f.cpu() - ref["weights"]).abs().max().item()
     print(f"[parity] {name} teacher-forced rgb: coarse {d0:.2e} fine {d1:.2e} weights {dw:.2e}")
     parity_log.record(f"{name}[teacher-forced]", rgb0_max=d0, rgb_map_max=d1, weights_max=dw)
-    assert d0 <= 4e-3 and d1 <= 4e-3
+    assert d0 <= 5e-5 and d1 <= 2e-3
 
 
 def test_stagewise_vs_oracle_and_ray_order():
