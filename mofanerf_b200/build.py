@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libmofa_b200.so")
-SOURCES = ["dense_tc.cu", "dense_tc2.cu", "coarse_fused.cu", "coarse_split.cu", "dense_wgrad.cu", "sampling.cu", "backward.cu",
+SOURCES = ["dense_tc.cu", "dense_tc2.cu", "coarse_fused.cu", "coarse_split.cu", "fine_chain.cu", "dense_wgrad.cu", "sampling.cu", "backward.cu",
            "engine.cu"]
 HEADERS = ["engine.h", "ptx.cuh", "pair.cuh", "dense_epilogue.cuh", os.path.join("..", "..", "include", "mofa_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -52,8 +52,11 @@ struct EpiGroup {
 // chunk are fetched while the chunk's TMEM load is in flight.  (Fetched where they are used — inside a branch on
 // p.head_n — every 8-column group exposed a full L1/L2 latency: ncu source page, 30 % of the sigma layer's time.)
 template <int BN, bool BWD, int HEAD, int NBUF>
+// hrow0: row of head_out that corresponds to the tile's first row (the fine-net chain kernel stores C into slab-local
+// buffers but writes head partials per global point row); the per-layer kernels pass m0.
 __device__ __forceinline__ void epilogue_tile_impl(const EpiParams& p, const void* tmC, uint32_t acc_addr,
-                                                   const EpiGroup& g, uint32_t& cnt, int m0, int n0, int row) {
+                                                   const EpiGroup& g, uint32_t& cnt, int m0, int n0, int row,
+                                                   long long hrow0) {
   float hacc[3] = {0.f, 0.f, 0.f};
   const float r1 = (BWD && p.r1_row != nullptr && m0 + row < p.M) ? p.r1_row[static_cast<size_t>(m0 + row) * p.r1_stride] : 0.0f;
 #pragma unroll 1
@@ -153,8 +156,8 @@ __device__ __forceinline__ void epilogue_tile_impl(const EpiParams& p, const voi
     }
   }
   if constexpr (HEAD > 0) {
-    if (m0 + row < p.M) {
-      float* dst = p.head_out + static_cast<size_t>(m0 + row) * p.head_stride + p.head_slot0 + g.slot * HEAD;
+    if (hrow0 + row < p.M) {
+      float* dst = p.head_out + static_cast<size_t>(hrow0 + row) * p.head_stride + p.head_slot0 + g.slot * HEAD;
 #pragma unroll
       for (int q = 0; q < HEAD; ++q) dst[q] = hacc[q];
     }
@@ -163,13 +166,14 @@ __device__ __forceinline__ void epilogue_tile_impl(const EpiParams& p, const voi
 
 template <int BN, bool BWD, int NBUF>
 __device__ __forceinline__ void epilogue_tile(const EpiParams& p, const void* tmC, uint32_t acc_addr, const EpiGroup& g,
-                                              uint32_t& cnt, int m0, int n0, int row) {
+                                              uint32_t& cnt, int m0, int n0, int row, long long hrow0 = -1) {
+  if (hrow0 < 0) hrow0 = m0;
   if constexpr (BWD) {
-    epilogue_tile_impl<BN, BWD, 0, NBUF>(p, tmC, acc_addr, g, cnt, m0, n0, row);
+    epilogue_tile_impl<BN, BWD, 0, NBUF>(p, tmC, acc_addr, g, cnt, m0, n0, row, hrow0);
   } else {
-    if (p.head_n == 0) epilogue_tile_impl<BN, BWD, 0, NBUF>(p, tmC, acc_addr, g, cnt, m0, n0, row);
-    else if (p.head_n == 1) epilogue_tile_impl<BN, BWD, 1, NBUF>(p, tmC, acc_addr, g, cnt, m0, n0, row);
-    else epilogue_tile_impl<BN, BWD, 3, NBUF>(p, tmC, acc_addr, g, cnt, m0, n0, row);
+    if (p.head_n == 0) epilogue_tile_impl<BN, BWD, 0, NBUF>(p, tmC, acc_addr, g, cnt, m0, n0, row, hrow0);
+    else if (p.head_n == 1) epilogue_tile_impl<BN, BWD, 1, NBUF>(p, tmC, acc_addr, g, cnt, m0, n0, row, hrow0);
+    else epilogue_tile_impl<BN, BWD, 3, NBUF>(p, tmC, acc_addr, g, cnt, m0, n0, row, hrow0);
   }
 }
 

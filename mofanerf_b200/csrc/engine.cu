@@ -116,6 +116,13 @@ struct mofa_b200_ctx {
   bool latents_set = false;
   bool pair_kernel = true;       // cta_group::2 kernel for N % 256 == 0 (MOFA_B200_DENSE_1CTA=1 disables)
   bool fused_coarse = true;      // one persistent kernel for a W == 256 net (MOFA_B200_NO_FUSED_COARSE=1 disables)
+  bool chain_fine = true;        // all dense layers of a W >= 512 net in one persistent launch, activations L2-resident
+                                 // (fine_chain.cu); MOFA_B200_FINE_PER_LAYER=1 selects one launch per layer (round 1)
+  // device tables of the chain kernel (tensor maps + layer descriptors), rebuilt when the buffers they point to change
+  CUtensorMap* chain_maps = nullptr;
+  mofa::ChainLayerDesc* chain_layers = nullptr;
+  const void* chain_key[4] = {nullptr, nullptr, nullptr, nullptr};
+  mofa::ChainParams chain_proto;
   bool split_coarse = true;      // ... in split precision (fp16 hi+lo, 3 products): MOFA_B200_COARSE_FP16=1 selects the
                                  // single-fp16 fused kernel of round 1 instead
   int64_t launches = 0;
@@ -353,6 +360,8 @@ struct Workspace {
   __half* X0lo;        // split-precision coarse kernel: low image of the point encoding [P_pad, 64]
   float* ray_vec;      // ... per-ray view vector [groups, 128]
   float* park;         // ... parked fp32 skip partial products, one [128 x 256] block per CTA
+  uint32_t* chain_ctr; // fine-net chain kernel: per (layer, m-block) completion counters
+  int64_t t_rows;      // rows of each activation buffer T[i] (== P_pad, or a few slabs when the chain kernel is in use)
   int64_t P_pad;
   size_t total;
 };
@@ -364,10 +373,32 @@ struct ViewSrc {
   int rows_per_group;
 };
 
-Workspace carve(void* base, int64_t n_chunk, int S_c, int S_f, int Wmax) {
+constexpr int kChainMaxLayers = 40;
+constexpr int64_t kSmallRows = 65536;     // activation-buffer rows kept for the per-layer / SIMT paths when the chain kernel is on
+
+// Rows of the three rotating activation buffers.  With the chain kernel the fine net only ever touches one slab of them
+// (that is the point: they stay in L2), so a chunk may be arbitrarily long without growing them; the per-layer paths
+// (SIMT verification, MOFA_B200_FINE_PER_LAYER / NO_FUSED_COARSE) need one row per point.
+int64_t t_rows_for(const mofa_b200_ctx* c, int64_t P_pad) {
+  if (c == nullptr) return P_pad;     // training workspaces: activations are kept per layer elsewhere
+  bool chain = c->chain_fine && c->pair_kernel && c->fused_coarse;
+  bool any = false;
+  for (int i = 0; i < 2; ++i)
+    if (c->nets[i].loaded && c->nets[i].W >= 512) {
+      any = true;
+      if (c->nets[i].W % 512 != 0 || c->nets[i].W > 1024) chain = false;
+    }
+  if (!chain || !any) return P_pad;
+  const int64_t slab = static_cast<int64_t>(kChainSlabMb) * 256;
+  const int64_t small = P_pad < kSmallRows ? P_pad : kSmallRows;
+  return small > slab ? small : slab;
+}
+
+Workspace carve(const mofa_b200_ctx* c, void* base, int64_t n_chunk, int S_c, int S_f, int Wmax) {
   Workspace w;
   const int S_max = S_f > S_c ? S_f : S_c;
   w.P_pad = (n_chunk * S_max + 127) / 128 * 128;
+  w.t_rows = t_rows_for(c, w.P_pad);
   size_t off = 0;
   auto take = [&](size_t bytes) {
     size_t o = off;
@@ -382,11 +413,12 @@ Workspace carve(void* base, int64_t n_chunk, int S_c, int S_f, int Wmax) {
   w.hp = reinterpret_cast<float*>(b + take(sizeof(float) * kHeadStride * w.P_pad));
   w.X0 = reinterpret_cast<__half*>(b + take(sizeof(__half) * 64 * w.P_pad));
   w.V = reinterpret_cast<__half*>(b + take(sizeof(__half) * 64 * w.P_pad));
-  for (int i = 0; i < 3; ++i) w.T[i] = reinterpret_cast<__half*>(b + take(sizeof(__half) * (size_t)Wmax * w.P_pad));
+  for (int i = 0; i < 3; ++i) w.T[i] = reinterpret_cast<__half*>(b + take(sizeof(__half) * (size_t)Wmax * w.t_rows));
   w.fscratch = reinterpret_cast<__half*>(b + take(sizeof(__half) * 256 * 128 * kMaxSms));
   w.X0lo = reinterpret_cast<__half*>(b + take(sizeof(__half) * 64 * w.P_pad));
   w.ray_vec = reinterpret_cast<float*>(b + take(sizeof(float) * 128 * n_chunk));
   w.park = reinterpret_cast<float*>(b + take(coarse_split_park_bytes(kMaxSms)));
+  w.chain_ctr = reinterpret_cast<uint32_t*>(b + take(sizeof(uint32_t) * kChainMaxLayers * (w.P_pad / 256 + 1)));
   w.total = off;
   return w;
 }
@@ -399,6 +431,134 @@ int max_width(mofa_b200_ctx* c) {
 }
 
 // Runs the MLP program of `net` over the first P_pad rows of the workspace buffers.
+
+// All dense layers of a wide net (W = 512 or 1024) in ONE persistent launch with L2-resident activations (fine_chain.cu).
+// The tensor-map / layer tables live in device memory and are rebuilt only when the buffers they describe change.
+bool chain_applies(const mofa_b200_ctx* c, const Net& net) {
+  return c->chain_fine && c->pair_kernel && net.W >= 512 && net.W % 512 == 0 && net.W <= 1024 &&
+         static_cast<int>(net.layers.size()) <= kChainMaxLayers;
+}
+
+int run_chain(mofa_b200_ctx* c, Net& net, const Workspace& ws, int64_t P_rows, cudaStream_t s) {
+  const int net_id = static_cast<int>(&net - c->nets);
+  const int64_t slab_rows = static_cast<int64_t>(kChainSlabMb) * 256;
+  if (ws.t_rows < slab_rows) return fail("chain kernel: activation buffers have %lld rows, need %lld", (long long)ws.t_rows, (long long)slab_rows);
+  const void* key[4] = {ws.T[0], ws.X0, ws.V, &net};
+  if (c->chain_maps == nullptr) {
+    CK(cudaMalloc(reinterpret_cast<void**>(&c->chain_maps), sizeof(CUtensorMap) * kChainMaxLayers * 5));
+    CK(cudaMalloc(reinterpret_cast<void**>(&c->chain_layers), sizeof(ChainLayerDesc) * kChainMaxLayers));
+  }
+  if (memcmp(key, c->chain_key, sizeof(key)) != 0) {
+    std::vector<CUtensorMap> maps;
+    std::vector<ChainLayerDesc> descs;
+    auto src_map = [&](int id, int K, int* is_global) -> int {
+      CUtensorMap m;
+      int rc;
+      if (id == SRC_X0 || id == SRC_V) {
+        *is_global = 1;
+        rc = make_tmap_2d(c, &m, id == SRC_X0 ? ws.X0 : ws.V, (uint64_t)ws.P_pad, 64, 64, 128);
+      } else {
+        *is_global = 0;
+        rc = make_tmap_2d(c, &m, ws.T[id - SRC_T0], (uint64_t)slab_rows, (uint64_t)K, (uint64_t)K, 128);
+      }
+      if (rc) return -1;
+      maps.push_back(m);
+      return static_cast<int>(maps.size()) - 1;
+    };
+    const int pair_groups = 2;
+    int tiles_per_mb = 0, nt = 0, nt_last = 0;
+    for (const Step& st : net.program) {
+      if (st.kind != 0) continue;
+      const Layer& L = net.layers[st.layer];
+      ChainLayerDesc d;
+      memset(&d, 0, sizeof(d));
+      d.kb0 = L.K[0] / 64;
+      d.kb1 = L.nseg > 1 ? L.K[1] / 64 : 0;
+      d.n_tiles = L.N / 256;
+      d.N = L.N;
+      d.bias = L.bias_eff;
+      d.relu = 1;
+      d.store_c = 1;
+      if ((d.mapA0 = src_map(st.in[0], L.K[0], &d.a0_global)) < 0) return 1;
+      maps.push_back(L.tmB2[0]);
+      d.mapB0 = static_cast<int>(maps.size()) - 1;
+      d.mapA1 = d.mapA0;
+      d.mapB1 = d.mapB0;
+      if (L.nseg > 1) {
+        if ((d.mapA1 = src_map(st.in[1], L.K[1], &d.a1_global)) < 0) return 1;
+        maps.push_back(L.tmB2[1]);
+        d.mapB1 = static_cast<int>(maps.size()) - 1;
+      }
+      if (st.head == 1) {
+        d.head_w = net.w_alpha; d.head_n = 1; d.head_slot0 = 0;
+      } else if (st.head == 2) {
+        d.head_w = net.w_rgb; d.head_n = 3; d.head_slot0 = kRgbSlot0;
+        d.store_c = 0;                       // the view layer feeds rgb_linear only
+      }
+      {
+        CUtensorMap m;
+        if (make_tmap_2d(c, &m, ws.T[st.out - SRC_T0], (uint64_t)slab_rows, (uint64_t)L.N, (uint64_t)L.N, 128)) return 1;
+        maps.push_back(m);
+        d.mapC = static_cast<int>(maps.size()) - 1;
+      }
+      tiles_per_mb += d.n_tiles;
+      descs.push_back(d);
+    }
+    const int nl = static_cast<int>(descs.size());
+    if (nl < 2 || nl > kChainMaxLayers || static_cast<int>(maps.size()) > kChainMaxLayers * 5) return fail("chain kernel: unsupported program");
+    nt = descs[0].n_tiles;
+    nt_last = descs[nl - 1].n_tiles;
+    for (int i = 0; i < nl - 1; ++i)
+      if (descs[i].n_tiles != nt) return fail("chain kernel: layers of different widths");
+    if (nt * pair_groups > 8 || nt_last * pair_groups * 3 > kHeadStride - kRgbSlot0) return fail("chain kernel: head slots do not fit");
+    CK(cudaMemcpyAsync(c->chain_maps, maps.data(), sizeof(CUtensorMap) * maps.size(), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(c->chain_layers, descs.data(), sizeof(ChainLayerDesc) * nl, cudaMemcpyHostToDevice, s));
+    CK(cudaStreamSynchronize(s));            // the host vectors go out of scope; happens once per (workspace, net)
+    memcpy(c->chain_key, key, sizeof(key));
+    ChainParams& P = c->chain_proto;
+    memset(&P, 0, sizeof(P));
+    P.maps = c->chain_maps;
+    P.layers = c->chain_layers;
+    P.n_layers = nl;
+    P.nt = nt;
+    P.nt_last = nt_last;
+    P.tiles_per_mb = tiles_per_mb;
+    P.slab_mb = kChainSlabMb;
+    P.head_stride = kHeadStride;
+  }
+  ChainParams P = c->chain_proto;
+  P.total_mb = static_cast<int>((P_rows + 255) / 256);
+  P.head_out = ws.hp;
+  P.P_rows = P_rows;
+  P.counters = ws.chain_ctr;
+  CK(cudaMemsetAsync(ws.chain_ctr, 0, sizeof(uint32_t) * (size_t)P.n_layers * P.total_mb, s));
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (c->profiling) {
+    const size_t idx = c->recs.size() * 2;
+    while (c->ev.size() < idx + 2) {
+      cudaEvent_t e;
+      CK(cudaEventCreate(&e));
+      c->ev.push_back(e);
+    }
+    e0 = c->ev[idx];
+    e1 = c->ev[idx + 1];
+    CK(cudaEventRecord(e0, s));
+  }
+  CK(launch_fine_chain(P, c->num_sms, s));
+  if (c->profiling) {
+    double fl = 0.0;
+    for (const Step& st : net.program)
+      if (st.kind == 0) fl += 2.0 * (double)P_rows * (double)net.layers[st.layer].N * (double)net.layers[st.layer].in_ref;
+    CK(cudaEventRecord(e1, s));
+    c->recs.push_back({net_id, fl});
+  }
+  c->launches++;
+  const int a_slots = (net.W / 256) * 2, r_slots = (net.W / 2 / 256) * 2;
+  CK(launch_finalize_raw(ws.hp, kHeadStride, 0, a_slots, kRgbSlot0, r_slots, net.b_alpha, net.b_rgb, ws.raw, P_rows, s));
+  c->launches++;
+  return 0;
+}
+
 // True when `net` runs in the split-precision fused kernel for an inference pass (the caller must then have produced the
 // low image of the point encoding, ws.X0lo).
 bool use_split(const mofa_b200_ctx* c, const Net& net, uint32_t flags) {
@@ -490,6 +650,10 @@ int run_program(mofa_b200_ctx* c, Net& net, const Workspace& ws, int64_t P_rows,
     c->launches++;
     return 0;
   }
+  if (tc && !act && chain_applies(c, net)) return run_chain(c, net, ws, P_rows, s);
+  if (M > ws.t_rows && !act)
+    return fail("the per-layer path needs %lld activation rows but the workspace keeps %lld (chain-kernel layout): render "
+                "fewer rays per call or set chunk_rays", (long long)M, (long long)ws.t_rows);
   // head fusion needs every partial slot to fit: W/256 alpha tiles (<= 4), (W/2)/BN rgb tiles (<= 4)
   const int a_tiles = net.W / 256;
   const int r_bn = ((net.W / 2) % 256 == 0) ? 256 : 128;
@@ -611,6 +775,9 @@ int mofa_b200_create(mofa_b200_ctx** out, int device) {
     c->pair_kernel = !(v && v[0] == '1');
     v = getenv("MOFA_B200_NO_FUSED_COARSE");
     c->fused_coarse = !(v && v[0] == '1');
+    v = getenv("MOFA_B200_FINE_PER_LAYER");
+    c->chain_fine = !(v && v[0] == '1');
+    if (e == cudaSuccess) e = mofa::fine_chain_configure();
     v = getenv("MOFA_B200_COARSE_FP16");
     c->split_coarse = !(v && v[0] == '1');
     if (e == cudaSuccess) e = mofa::coarse_fused_configure();
@@ -639,6 +806,8 @@ int mofa_b200_destroy(mofa_b200_ctx* c) {
   for (int i = 0; i < 2; ++i) free_net(c->nets[i]);
   for (int i = 1; i < 4; ++i) cudaFree(c->lat[i]);
   for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
+  cudaFree(c->chain_maps);
+  cudaFree(c->chain_layers);
   delete c;
   return 0;
 }
@@ -908,7 +1077,7 @@ size_t mofa_b200_workspace_bytes(mofa_b200_ctx* c, int64_t n_rays, int n_samples
   const int S_f = n_importance > 0 ? n_samples + n_importance : 0;
   int Wmax = max_width(c);
   if (Wmax == 0) Wmax = 1024;
-  return carve(nullptr, ch, n_samples, S_f, Wmax).total + 1024;
+  return carve(c, nullptr, ch, n_samples, S_f, Wmax).total + 1024;
 }
 
 int mofa_b200_render_rays_fwd(mofa_b200_ctx* c, const mofa_b200_render_args* a, void* stream) {
@@ -932,12 +1101,13 @@ int mofa_b200_render_rays_fwd(mofa_b200_ctx* c, const mofa_b200_render_args* a, 
   CK(cudaSetDevice(c->device));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
 
-  const int ch = effective_chunk(a->n_rays, a->chunk_rays);
+  int ch = effective_chunk(a->n_rays, a->chunk_rays);
+  if ((a->flags & MOFA_FLAG_GEMM_SIMT) && ch > 256) ch = 256;    // verification path: per-layer buffers, one row per point
   const int Wmax = max_width(c);
   if (!a->workspace) return fail("render_rays_fwd: workspace is NULL");
   uint8_t* wbase = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<size_t>(a->workspace), 1024));
   const size_t slack = wbase - static_cast<uint8_t*>(a->workspace);
-  Workspace ws = carve(wbase, ch, S_c, S_f, Wmax);
+  Workspace ws = carve(c, wbase, ch, S_c, S_f, Wmax);
   if (ws.total + slack > a->workspace_bytes)
     return fail("render_rays_fwd: workspace too small (%zu < %zu)", a->workspace_bytes, ws.total + slack);
   const int lindisp = (a->flags & MOFA_FLAG_LINDISP) ? 1 : 0;
@@ -1006,7 +1176,7 @@ size_t mofa_b200_query_workspace_bytes(mofa_b200_ctx* c, int64_t n_pts) {
   if (!c) return 0;
   int Wmax = max_width(c);
   if (Wmax == 0) Wmax = 1024;
-  return carve(nullptr, n_pts, 1, 0, Wmax).total + 1024;
+  return carve(c, nullptr, n_pts, 1, 0, Wmax).total + 1024;
 }
 
 int mofa_b200_run_network(mofa_b200_ctx* c, int net_id, const float* pts, const float* viewdirs, int64_t n_pts,
@@ -1020,7 +1190,7 @@ int mofa_b200_run_network(mofa_b200_ctx* c, int net_id, const float* pts, const 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   uint8_t* wbase = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<size_t>(workspace), 1024));
   const size_t slack = wbase - static_cast<uint8_t*>(workspace);
-  Workspace ws = carve(wbase, n_pts, 1, 0, max_width(c));
+  Workspace ws = carve(c, wbase, n_pts, 1, 0, max_width(c));
   if (ws.total + slack > workspace_bytes)
     return fail("run_network: workspace too small (%zu < %zu)", workspace_bytes, ws.total + slack);
   {
@@ -1142,7 +1312,7 @@ int n_dense_steps(const Net& n) {
 TrainWS carve_train(void* base, int64_t n, int S_c, int S_f, const Net& nc, const Net* nf) {
   TrainWS t;
   const int Wmax = nf && nf->W > nc.W ? nf->W : nc.W;
-  t.fw = carve(base, n, S_c, S_f, Wmax);
+  t.fw = carve(nullptr, base, n, S_c, S_f, Wmax);
   size_t off = align_up(t.fw.total, 1024);
   uint8_t* b = static_cast<uint8_t*>(base);
   auto take = [&](size_t bytes) {

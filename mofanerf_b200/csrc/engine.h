@@ -142,6 +142,35 @@ cudaError_t launch_view_vec(const float* dirs, int stride, int64_t n, const floa
 cudaError_t launch_pack_weight_lo(const float* src, int ld, int c0, int k, int kpad, int nrows, __half* dst,
                                   cudaStream_t s);
 
+// ---- fine-net chain kernel (fine_chain.cu): all dense layers of a W >= 512 net in one persistent launch -------------
+struct ChainLayerDesc {
+  int mapA0, mapA1, mapB0, mapB1, mapC;   // indices into ChainParams::maps
+  int kb0, kb1;                           // 64-wide K blocks per segment
+  int n_tiles;                            // N / 256
+  int a0_global, a1_global;               // A rows: 1 = global point rows (encodings), 0 = slab-local activation buffers
+  int relu, store_c;
+  int head_n, head_slot0;                 // fused output head (0 = none)
+  int N;
+  const float* bias;
+  const float* head_w;
+};
+struct ChainParams {
+  const CUtensorMap* maps;                // device array
+  const ChainLayerDesc* layers;           // device array
+  int n_layers;
+  int nt, nt_last;                        // n-tiles of every layer but the last / of the last layer
+  int tiles_per_mb;                       // sum of n_tiles over the layers
+  int slab_mb;                            // m-blocks (256 rows) per slab
+  int total_mb;                           // ceil(P_rows / 256)
+  float* head_out;                        // [P_rows, head_stride] head partial slots
+  int head_stride;
+  int64_t P_rows;
+  uint32_t* counters;                     // [n_layers, total_mb], zero before the launch
+};
+cudaError_t launch_fine_chain(const ChainParams& p, int num_sms, cudaStream_t stream);
+cudaError_t fine_chain_configure();
+constexpr int kChainSlabMb = 37;          // 37 m-blocks x 4 n-tiles = two rounds of the 74 CTA pairs per layer
+
 // ---- backward pass (backward.cu) ----------------------------------------------------------------
 cudaError_t launch_composite_bwd(const float* raw, const float* z, const float* rays, int stride, const float* noise,
                                  const float* d_rgb, const float* d_acc, float gscale, int64_t n, int S,

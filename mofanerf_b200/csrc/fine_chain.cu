@@ -1,0 +1,301 @@
+// Fine network as ONE persistent kernel per pass: all dense layers of a W >= 512 net (27 nn.Linear of the W = 1024 fine
+// net: models/model.py:121-137, 226-230) chained inside a single launch of 74 CTA pairs, activations L2-resident.
+//
+// Why: launched layer by layer over a 4144-ray chunk, every 1024 -> 1024 layer streams its 1.09 GB input from HBM and its
+// 1.05 GB output back (ncu: 2.14 GB DRAM traffic per 1.11-TFLOP launch, 2.8 TB/s) — not time-limiting (DRAM 36 %), but the
+// GPU sits at its 1 kW power cap and every HBM byte is paid for in SM clock (round-1 verdict: 0.80 pJ/FLOP against cuBLAS's
+// 0.73).  The only traffic the algorithm needs is 365 KB of rays per chunk.
+//
+// How: the point rows are processed in SLABS of 37 m-blocks (9472 rows = 74 rays x 128 samples).  For one slab the
+// three rotating activation buffers are 3 x 19.4 MB — together with the weights they fit the 126 MB L2 — and every slab
+// re-uses the SAME physical buffers, so activations are written and read back through L2 without ever having to reach
+// HBM.  Work item = (slab, layer, m-block, n-tile) = one 256 x 256 output tile of one layer; items are numbered slab-major,
+// then layer, then m-block, then n-tile, and pair p takes items p, p + 74, p + 148, ... — a layer of a full slab is
+// exactly two rounds of the 74 pairs.  A tile of layer l needs the four n-tiles of layer l-1 of ITS m-block only, which
+// lie two rounds back in that order: by the time a pair's producer warp polls the m-block's completion counter
+// (ld.acquire.gpu) it is almost always already there.  Counters are bumped by the epilogue (red.release.gpu) after the
+// tile's TMA stores have completed (cp.async.bulk.wait_group 0) and a proxy fence; the consumer fences the async proxy
+// again before its TMA loads.  Layer 0 of slab s waits for the last layer of slab s-1 at the same local m-block (the
+// buffers it overwrites are free then).  Every dependency points to a lower item number and all 74 pairs are co-resident,
+// so the pair holding the lowest unfinished item can always run: no deadlock.
+//
+// The tile pipeline itself is the CTA-pair kernel of dense_tc2.cu (cta_group::2 UMMA 256x256x16, 6-stage TMA ring,
+// double-buffered TMEM accumulators, 8 epilogue warps, fused alpha / rgb heads); what changes per tile are the tensor
+// maps (device array), the K extents, the bias / head pointers and the row coordinates (slab-local for the activation
+// buffers, global for the point encodings and the head partials).
+#include "dense_epilogue.cuh"
+#include "engine.h"
+#include "pair.cuh"
+#include "ptx.cuh"
+
+namespace mofa {
+
+constexpr int kChainStages = 6;
+
+struct ChainSmem {
+  static constexpr int A_BYTES = 128 * 64 * 2;
+  static constexpr int B_BYTES = 128 * 64 * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;          // per CTA
+  static constexpr int C_BYTES = 128 * 64 * 2;
+  static constexpr int OFF_C = kChainStages * STAGE_BYTES;
+  static constexpr int OFF_BAR = OFF_C + 2 * C_BYTES;            // one staging buffer per epilogue group
+  static constexpr int N_BARS = 2 * kChainStages + 4;
+  static constexpr int OFF_TPTR = OFF_BAR + N_BARS * 8;
+  static constexpr int TOTAL = OFF_TPTR + 16;
+  static constexpr int DYN_BYTES = TOTAL + 1024;
+};
+
+struct ChainTile {
+  int layer, mb_local, mb_global, n;
+};
+
+// item number -> (slab, layer, m-block, n-tile).  Every layer but the last has nt n-tiles, the last has nt_last
+// (checked on the host), so the layer follows from one division.
+__device__ __forceinline__ ChainTile chain_decode(const ChainParams& p, long long t) {
+  const int full = p.slab_mb * p.tiles_per_mb;
+  const int s = static_cast<int>(t / full);
+  const int r = static_cast<int>(t - static_cast<long long>(s) * full);
+  const int left = p.total_mb - s * p.slab_mb;
+  const int mb_s = left < p.slab_mb ? left : p.slab_mb;
+  const int q = r / mb_s;                                   // in units of "n-tiles of one m-block"
+  int l = q / p.nt;
+  if (l > p.n_layers - 1) l = p.n_layers - 1;
+  const int ntl = (l == p.n_layers - 1) ? p.nt_last : p.nt;
+  const int r2 = r - l * p.nt * mb_s;
+  ChainTile c;
+  c.layer = l;
+  c.mb_local = r2 / ntl;
+  c.n = r2 - c.mb_local * ntl;
+  c.mb_global = s * p.slab_mb + c.mb_local;
+  return c;
+}
+
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(uint32_t* p, uint32_t v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// Bounded spin on an m-block's completion counter (a protocol bug must trap, not hang the box).
+__device__ __forceinline__ void wait_counter(const uint32_t* ctr, uint32_t need) {
+  uint32_t spins = 0;
+  long long t0 = 0;
+  while (ld_acquire_gpu(ctr) < need) {
+    __nanosleep(64);
+    if ((++spins & 0x3FFu) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ll) __trap();
+    }
+  }
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
+fine_chain_kernel(const ChainParams p) {
+  using L = ChainSmem;
+  constexpr int STAGES = kChainStages;
+  constexpr int BN = 256;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - raw_addr);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const uint32_t full0 = base + L::OFF_BAR;            // used in the leader only (bytes of both CTAs)
+  const uint32_t empty0 = full0 + 8 * STAGES;          // per CTA
+  const uint32_t tfull0 = empty0 + 8 * STAGES;         // per CTA
+  const uint32_t tempty0 = tfull0 + 16;                // used in the leader only (8 warp arrivals per CTA)
+  const uint32_t tptr = base + L::OFF_TPTR;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(full0 + 8 * i, 1);
+      mbar_init(empty0 + 8 * i, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(tfull0 + 8 * i, 1);
+      mbar_init(tempty0 + 8 * i, 16);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) {
+    tmem_alloc_cg2(tptr, 512);
+    tmem_relinquish_cg2();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(base_ptr + L::OFF_TPTR);
+
+  const long long num_items = static_cast<long long>(p.total_mb) * p.tiles_per_mb;
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+
+  if (warp < 4) {
+    setmaxnreg_dec_40();
+    if (warp == 0) {
+      // ------------------------------------------------------------------ TMA producer (both CTAs)
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long t = pair; t < num_items; t += num_pairs) {
+        const ChainTile c = chain_decode(p, t);
+        const ChainLayerDesc d = p.layers[c.layer];
+        // dependency: the previous layer's n-tiles of this m-block (or, for layer 0 of a later slab, the last layer of
+        // the previous slab at the same local m-block: the activation buffers it still reads are overwritten from here on)
+        if (lane == 0) {
+          if (c.layer > 0) {
+            wait_counter(p.counters + static_cast<size_t>(c.layer - 1) * p.total_mb + c.mb_global, 4u * p.nt);
+          } else if (c.mb_global >= p.slab_mb) {
+            wait_counter(p.counters + static_cast<size_t>(p.n_layers - 1) * p.total_mb + (c.mb_global - p.slab_mb),
+                         4u * p.nt_last);
+          }
+        }
+        __syncwarp();
+        fence_proxy_async_all();      // the loads below are async-proxy reads of data other CTAs' TMA stores wrote
+        const int ml = c.mb_local * 256 + static_cast<int>(rank) * 128;
+        const int mg = c.mb_global * 256 + static_cast<int>(rank) * 128;
+        const int m_a0 = d.a0_global ? mg : ml;
+        const int m_a1 = d.a1_global ? mg : ml;
+        const int n0 = c.n * BN + static_cast<int>(rank) * 128;
+        const int total_kb = d.kb0 + d.kb1;
+        for (int kb = 0; kb < total_kb; ++kb) {
+          mbar_wait(empty0 + 8 * stage, phase ^ 1u);
+          const uint32_t fb_local = full0 + 8 * stage;
+          const uint32_t fb = mapa_u32(fb_local, 0);
+          const uint32_t sa = base + stage * L::STAGE_BYTES;
+          const uint32_t sb = sa + L::A_BYTES;
+          if (elect_one()) {
+            if (leader) mbar_expect_tx(fb_local, 2 * L::STAGE_BYTES);
+            if (kb < d.kb0) {
+              tma_load_2d_cg2(sa, p.maps + d.mapA0, fb, kb * 64, m_a0);
+              tma_load_2d_cg2(sb, p.maps + d.mapB0, fb, kb * 64, n0);
+            } else {
+              const int k = (kb - d.kb0) * 64;
+              tma_load_2d_cg2(sa, p.maps + d.mapA1, fb, k, m_a1);
+              tma_load_2d_cg2(sb, p.maps + d.mapB1, fb, k, n0);
+            }
+          }
+          __syncwarp();
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    } else if (warp == 1 && leader) {
+      // ------------------------------------------------------------------ MMA issuer (leader CTA)
+      constexpr uint32_t idesc = umma_idesc_f16_f32(256, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (long long t = pair; t < num_items; t += num_pairs, ++it) {
+        const ChainTile c = chain_decode(p, t);
+        const ChainLayerDesc d = p.layers[c.layer];
+        const int total_kb = d.kb0 + d.kb1;
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(tempty0 + 8 * as, aphase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < total_kb; ++kb) {
+          mbar_wait(full0 + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t sa = base + stage * L::STAGE_BYTES;
+          const uint64_t da = umma_desc_sw128_kmajor(sa);
+          const uint64_t db = umma_desc_sw128_kmajor(sa + L::A_BYTES);
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_f16_ss_cg2(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit_cg2_mc(empty0 + 8 * stage, 0x3);
+            if (kb == total_kb - 1) umma_commit_cg2_mc(tfull0 + 8 * as, 0x3);
+          }
+          __syncwarp();
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (both CTAs, own 128 rows; two column groups)
+    setmaxnreg_inc_232();
+    const int ew = warp & 3;
+    const int grp = (warp - 4) >> 2;
+    const int row = ew * 32 + lane;
+    const uint32_t lane_base = static_cast<uint32_t>(ew * 32) << 16;
+    EpiGroup g;
+    g.cbuf0 = base + L::OFF_C + grp * L::C_BYTES;
+    g.cb0 = grp * 2;
+    g.cb1 = g.cb0 + 2;
+    g.bar_id = 1 + grp;
+    g.gtid = static_cast<int>(threadIdx.x) - 128 - grp * 128;
+    int it = 0;
+    uint32_t cnt = 0;
+    for (long long t = pair; t < num_items; t += num_pairs, ++it) {
+      const ChainTile c = chain_decode(p, t);
+      const ChainLayerDesc d = p.layers[c.layer];
+      EpiParams e;
+      e.bias = d.bias;
+      e.head_w = d.head_w;
+      e.head_out = p.head_out;
+      e.relu = d.relu;
+      e.store_c = d.store_c;
+      e.head_n = d.head_n;
+      e.head_stride = p.head_stride;
+      e.head_slot0 = d.head_slot0;
+      e.N = d.N;
+      e.M = static_cast<int>(p.P_rows);
+      e.mask = nullptr;
+      e.r1_row = nullptr;
+      e.r1_col = nullptr;
+      e.r1_stride = 0;
+      const int ml = c.mb_local * 256 + static_cast<int>(rank) * 128;
+      const long long mg = static_cast<long long>(c.mb_global) * 256 + static_cast<long long>(rank) * 128;
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      g.slot = c.n * 2 + grp;
+      mbar_wait(tfull0 + 8 * as, aphase);
+      tc_fence_after();
+      epilogue_tile<BN, false, 1>(e, p.maps + d.mapC, tmem_base + lane_base + as * BN, g, cnt, ml, c.n * BN, row, mg);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(tempty0 + 8 * as, 0));
+      // publish: this group's part of the tile (128 rows x 128 columns) is in global memory.  Thread 0 of the group issued
+      // the TMA stores: wait for their completion (writes performed, not just the staging buffer read), order them before
+      // the counter update across proxies, then release.
+      if (g.gtid == 0) {
+        tma_store_wait_all<0>();
+        fence_proxy_async_all();
+        red_release_gpu_add(p.counters + static_cast<size_t>(c.layer) * p.total_mb + c.mb_global, 1u);
+      }
+    }
+  }
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) tmem_dealloc_cg2(tmem_base, 512);
+}
+
+cudaError_t fine_chain_configure() {
+  return cudaFuncSetAttribute(fine_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ChainSmem::DYN_BYTES);
+}
+
+cudaError_t launch_fine_chain(const ChainParams& p, int num_sms, cudaStream_t stream) {
+  const long long items = static_cast<long long>(p.total_mb) * p.tiles_per_mb;
+  if (items <= 0) return cudaSuccess;
+  const int max_pairs = num_sms / 2;
+  const int pairs = static_cast<int>(items < max_pairs ? items : max_pairs);
+  fine_chain_kernel<<<2 * pairs, 384, ChainSmem::DYN_BYTES, stream>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace mofa
