@@ -160,6 +160,19 @@ typedef struct mofa_b200_bwd_args {
 
 int mofa_b200_render_rays_bwd(mofa_b200_ctx* ctx, const mofa_b200_bwd_args* args, void* stream);
 
+/*
+ * get_rays (tools/run_nerf_helpers.py:153-168) + the ray-batch packing at the top of myRenderer.render /
+ * render_fitting (models/render_class.py:158-179, 393-415), SURVEY.md §8 row f3: the rays of the row-major range
+ * [first_ray, first_ray + n_rays) of an H x W pinhole image, generated on the device from 21 scalars — K (HOST, 3x3
+ * row-major: fx = K[0], cx = K[2], fy = K[4], cy = K[5]), c2w (HOST, [3,4] row-major), near, far — so a frame needs no
+ * host->device input and every rank of a ray-sharded render produces only its own range.  rays_out [n_rays, ray_stride]
+ * (device): o(3) d(3) near far viewdir(3); ray_stride >= 11, and 12 gives 16-byte rows that every kernel reads with
+ * 128-bit loads.  fp32 operation order as torch evaluates get_rays: bit-identical origins and directions.
+ */
+int mofa_b200_generate_rays(mofa_b200_ctx* ctx, int H, int W, const float* K9, const float* c2w12, float near_,
+                            float far_, int64_t first_ray, int64_t n_rays, float* rays_out, int ray_stride,
+                            void* stream);
+
 /* ---- op-level entry points (each one is also a stage of render_rays_fwd) ---- */
 
 /* Embedder.embed (models/model.py:15-63): x [n,3] fp32 -> out [n, 3+6*multires] fp32. */

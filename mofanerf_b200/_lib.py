@@ -66,6 +66,8 @@ SIGNATURES = {
     "mofa_b200_query_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int64]),
     "mofa_b200_run_network": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                                         C.c_uint32, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "mofa_b200_generate_rays": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float,
+                                          C.c_float, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_void_p]),
     "mofa_b200_embed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
     "mofa_b200_raw2outputs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                         C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,

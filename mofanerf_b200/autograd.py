@@ -71,5 +71,8 @@ class RenderRaysFn(torch.autograd.Function):
             white_bkgd=cfg["white_bkgd"], lindisp=cfg["lindisp"], d_rgb=d_rgb, d_acc=d_acc,
             d_rgb0=d_rgb0 if ctx.fine else None, d_acc0=d_acc0 if ctx.fine else None, loss_scale=scale,
             param_grads=pg)
+        n_cols = ctx.saved["_rays"].shape[1]
+        if n_cols > 11:    # padded ray rows: the pad columns carry no gradient
+            d_rays = torch.cat([d_rays, d_rays.new_zeros(d_rays.shape[0], n_cols - 11)], 1)
         ctx.saved = None   # release the activation workspace
         return (d_rays, d_shape, d_exp, d_tex, None, None) + tuple(grads_p)

@@ -1206,6 +1206,22 @@ int mofa_b200_run_network(mofa_b200_ctx* c, int net_id, const float* pts, const 
   return 0;
 }
 
+int mofa_b200_generate_rays(mofa_b200_ctx* c, int H, int W, const float* K9, const float* c2w12, float near_, float far_,
+                            int64_t first_ray, int64_t n_rays, float* rays_out, int ray_stride, void* stream) {
+  if (!c) return fail("generate_rays: ctx is NULL");
+  if (!K9 || !c2w12 || !rays_out) return fail("generate_rays: NULL pointer");
+  if (H <= 0 || W <= 0 || ray_stride < 11) return fail("generate_rays: bad sizes (H=%d W=%d stride=%d)", H, W, ray_stride);
+  if (first_ray < 0 || n_rays < 0 || first_ray + n_rays > static_cast<int64_t>(H) * W)
+    return fail("generate_rays: ray range [%lld, %lld) outside the %dx%d image", (long long)first_ray,
+                (long long)(first_ray + n_rays), H, W);
+  if (K9[0] == 0.0f || K9[4] == 0.0f) return fail("generate_rays: zero focal length");
+  CK(cudaSetDevice(c->device));
+  CK(launch_generate_rays(H, W, K9, c2w12, near_, far_, first_ray, n_rays, rays_out, ray_stride,
+                          static_cast<cudaStream_t>(stream)));
+  c->launches++;
+  return 0;
+}
+
 int mofa_b200_embed(mofa_b200_ctx* c, const float* x, int64_t n, int multires, float* out, void* stream) {
   if (!c) return fail("embed: ctx is NULL");
   if (multires < 0 || multires > 16) return fail("embed: multires out of range");

@@ -60,6 +60,9 @@ cudaError_t launch_encode_rays(const float* rays, int stride, const float* z, in
 // explicit points (run_network): pts [P,3], viewdirs [P,3]
 cudaError_t launch_encode_points(const float* pts, const float* viewdirs, int64_t P, int multires,
                                  int multires_views, __half* X0, __half* V, cudaStream_t s, __half* X0lo = nullptr);
+// rays [n, stride] for the row-major ray range [first, first + n) of an H x W pinhole image (K9, c2w12: HOST arrays)
+cudaError_t launch_generate_rays(int H, int W, const float* K9, const float* c2w12, float nr, float fr, int64_t first,
+                                 int64_t n, float* rays, int stride, cudaStream_t s);
 cudaError_t launch_embed_f32(const float* x, int64_t n, int multires, float* out, cudaStream_t s);
 // out[p*4 + off + j] = A[p,:]·Wh[j,:] + b[j]    (alpha_linear / rgb_linear)
 cudaError_t launch_head(const __half* A, int K, const float* Wh, const float* b, int nout, float* raw,

@@ -70,26 +70,149 @@ __device__ __forceinline__ ChainTile chain_decode(const ChainParams& p, long lon
   return c;
 }
 
-__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+// Counter poll: a relaxed GPU-scope load (LDG.STRONG.GPU, served by L2).  ld.acquire.gpu would add a CCTL.IVALL — an
+// invalidation of the SM's whole L1 — to EVERY poll; the data the counter guards are read by TMA (async proxy, straight
+// from L2, never through L1), so the only ordering needed is "counter read before the TMA loads are issued": program
+// order of the issuing thread plus the proxy fence below.
+__device__ __forceinline__ uint32_t ld_relaxed_gpu(const uint32_t* p) {
   uint32_t v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ void red_release_gpu_add(uint32_t* p, uint32_t v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// generic <-> async proxy ordering for GLOBAL memory only (FENCE.VIEW.ASYNC.G; the unqualified form also emits a
+// GPU-scope MEMBAR)
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
 // Bounded spin on an m-block's completion counter (a protocol bug must trap, not hang the box).
 __device__ __forceinline__ void wait_counter(const uint32_t* ctr, uint32_t need) {
   uint32_t spins = 0;
   long long t0 = 0;
-  while (ld_acquire_gpu(ctr) < need) {
+  while (ld_relaxed_gpu(ctr) < need) {
     __nanosleep(64);
     if ((++spins & 0x3FFu) == 0) {
       const long long now = clock64();
       if (t0 == 0) t0 = now;
       else if (now - t0 > 4000000000ll) __trap();
+    }
+  }
+}
+
+
+// Epilogue of one tile for one epilogue group (4 warps x 32 rows, 128 of the tile's 256 columns = four 32-column chunks).
+// Same arithmetic and staging as dense_epilogue.cuh (bit-identical results) with one difference that matters here: the
+// bias of chunk q + 1 is fetched while chunk q is processed and chunk q's own fetches are issued before its TMEM wait.
+// In this kernel the SM's L1 is invalidated twice per tile (cp.async.bulk.wait_group before a tile is published), so
+// bias loads issued where they are used — fine in the per-layer kernels, where they hit L1 — each exposed an L2 round
+// trip: the epilogue became the critical path (tensor pipe 63 % active, ncu).
+template <int HEAD>
+__device__ __forceinline__ void chain_epilogue(const EpiParams& p, const void* tmC, uint32_t acc_addr, const EpiGroup& g,
+                                               int m0, int n0, int row, long long hrow0) {
+  float hacc[3] = {0.f, 0.f, 0.f};
+  const int col_base = n0 + g.cb0 * 64;
+  float4 bcur[8], bnext[8];
+  {
+    const float4* b4 = reinterpret_cast<const float4*>(p.bias + col_base);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) bcur[i] = ldg_f4_pinned(b4 + i);
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int cb = g.cb0 + (q >> 1), h = q & 1;
+    const int ncol = col_base + q * 32;
+    const uint32_t cbuf = g.cbuf0;
+    if (h == 0 && p.store_c) {
+      if (g.gtid == 0) tma_store_wait_read<0>();           // the store that last read the staging buffer is done
+      named_bar_sync(g.bar_id, 128);
+    }
+    uint32_t v[32];
+    tmem_ld_32x32b_x32(acc_addr + cb * 64 + h * 32, v);
+    constexpr int HB = (HEAD == 3) ? 1 : 4;           // 8-column blocks of head weights per fetch
+    constexpr int NHW = HEAD > 0 ? HEAD * 2 * HB : 1;
+    float4 hw[2][NHW];
+    if constexpr (HEAD > 0) {
+#pragma unroll
+      for (int qq = 0; qq < HEAD; ++qq) {
+        const float4* w4 = reinterpret_cast<const float4*>(p.head_w + static_cast<size_t>(qq) * p.N + ncol);
+#pragma unroll
+        for (int i = 0; i < 2 * HB; ++i) hw[0][qq * 2 * HB + i] = ldg_f4_pinned(w4 + i);
+      }
+    }
+    if constexpr (HEAD == 0) {        // (the head layers keep their registers for the head weights: own chunk only)
+      if (q + 1 < 4) {
+        const float4* b4 = reinterpret_cast<const float4*>(p.bias + ncol + 32);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) bnext[i] = ldg_f4_pinned(b4 + i);
+      }
+    } else if (q > 0) {
+      const float4* b4 = reinterpret_cast<const float4*>(p.bias + ncol);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) bcur[i] = ldg_f4_pinned(b4 + i);
+    }
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 b0 = bcur[2 * j], b1 = bcur[2 * j + 1];
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      float f[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float x = __uint_as_float(v[j * 8 + e]) + bb[e];
+        if (p.relu) x = fmaxf(x, 0.0f);
+        f[e] = fminf(fmaxf(x, -65504.0f), 65504.0f);
+      }
+      if constexpr (HEAD > 0 && HB == 1) {
+        if (j + 1 < 4) {
+#pragma unroll
+          for (int qq = 0; qq < HEAD; ++qq) {
+            const float4* w4 = reinterpret_cast<const float4*>(p.head_w + static_cast<size_t>(qq) * p.N + ncol) + 2 * (j + 1);
+            hw[(j + 1) & 1][qq * 2] = ldg_f4_pinned(w4);
+            hw[(j + 1) & 1][qq * 2 + 1] = ldg_f4_pinned(w4 + 1);
+          }
+        }
+      }
+      if constexpr (HEAD > 0) {
+#pragma unroll
+        for (int qq = 0; qq < HEAD; ++qq) {
+          const float4 w0 = HB == 1 ? hw[j & 1][qq * 2] : hw[0][qq * 2 * HB + 2 * j];
+          const float4 w1 = HB == 1 ? hw[j & 1][qq * 2 + 1] : hw[0][qq * 2 * HB + 2 * j + 1];
+          hacc[qq] += f[0] * w0.x + f[1] * w0.y + f[2] * w0.z + f[3] * w0.w + f[4] * w1.x + f[5] * w1.y +
+                      f[6] * w1.z + f[7] * w1.w;
+        }
+      }
+      if (p.store_c) {
+        __half2 h0 = __floats2half2_rn(f[0], f[1]);
+        __half2 h1 = __floats2half2_rn(f[2], f[3]);
+        __half2 h2 = __floats2half2_rn(f[4], f[5]);
+        __half2 h3 = __floats2half2_rn(f[6], f[7]);
+        const int chunk = h * 4 + j;              // 16-byte chunk within the 128-byte row
+        const uint32_t addr = cbuf + row * 128 + ((chunk ^ (row & 7)) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
+                     "r"(*reinterpret_cast<uint32_t*>(&h0)), "r"(*reinterpret_cast<uint32_t*>(&h1)),
+                     "r"(*reinterpret_cast<uint32_t*>(&h2)), "r"(*reinterpret_cast<uint32_t*>(&h3))
+                     : "memory");
+      }
+    }
+    if (h == 1 && p.store_c) {
+      fence_proxy_async_smem();
+      named_bar_sync(g.bar_id, 128);
+      if (g.gtid == 0) {
+        tma_store_2d(tmC, cbuf, n0 + cb * 64, m0);
+        tma_store_commit();
+      }
+    }
+    if constexpr (HEAD == 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) bcur[i] = bnext[i];
+    }
+  }
+  if constexpr (HEAD > 0) {
+    if (hrow0 + row < p.M) {
+      float* dst = p.head_out + static_cast<size_t>(hrow0 + row) * p.head_stride + p.head_slot0 + g.slot * HEAD;
+#pragma unroll
+      for (int qq = 0; qq < HEAD; ++qq) dst[qq] = hacc[qq];
     }
   }
 }
@@ -160,7 +283,7 @@ fine_chain_kernel(const ChainParams p) {
           }
         }
         __syncwarp();
-        fence_proxy_async_all();      // the loads below are async-proxy reads of data other CTAs' TMA stores wrote
+        fence_proxy_async_global();   // the loads below are async-proxy reads of data other CTAs' TMA stores wrote
         const int ml = c.mb_local * 256 + static_cast<int>(rank) * 128;
         const int mg = c.mb_global * 256 + static_cast<int>(rank) * 128;
         const int m_a0 = d.a0_global ? mg : ml;
@@ -240,7 +363,6 @@ fine_chain_kernel(const ChainParams p) {
     g.bar_id = 1 + grp;
     g.gtid = static_cast<int>(threadIdx.x) - 128 - grp * 128;
     int it = 0;
-    uint32_t cnt = 0;
     for (long long t = pair; t < num_items; t += num_pairs, ++it) {
       const ChainTile c = chain_decode(p, t);
       const ChainLayerDesc d = p.layers[c.layer];
@@ -266,7 +388,12 @@ fine_chain_kernel(const ChainParams p) {
       g.slot = c.n * 2 + grp;
       mbar_wait(tfull0 + 8 * as, aphase);
       tc_fence_after();
-      epilogue_tile<BN, false, 1>(e, p.maps + d.mapC, tmem_base + lane_base + as * BN, g, cnt, ml, c.n * BN, row, mg);
+      {
+        const uint32_t acc_addr = tmem_base + lane_base + as * BN;
+        if (d.head_n == 0) chain_epilogue<0>(e, p.maps + d.mapC, acc_addr, g, ml, c.n * BN, row, mg);
+        else if (d.head_n == 1) chain_epilogue<1>(e, p.maps + d.mapC, acc_addr, g, ml, c.n * BN, row, mg);
+        else chain_epilogue<3>(e, p.maps + d.mapC, acc_addr, g, ml, c.n * BN, row, mg);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_u32(tempty0 + 8 * as, 0));
@@ -275,7 +402,7 @@ fine_chain_kernel(const ChainParams p) {
       // the counter update across proxies, then release.
       if (g.gtid == 0) {
         tma_store_wait_all<0>();
-        fence_proxy_async_all();
+        fence_proxy_async_global();
         red_release_gpu_add(p.counters + static_cast<size_t>(c.layer) * p.total_mb + c.mb_global, 1u);
       }
     }

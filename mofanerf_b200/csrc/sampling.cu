@@ -51,6 +51,88 @@ __device__ __forceinline__ float linspace01(int i, int steps) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Ray rows: o(3) d(3) near far viewdir(3) [pad]   (models/render_class.py:176-179).  The reference's rows are 11
+// floats = 44 bytes; rows padded to 12 floats (what mofa_b200_generate_rays and the renderer's pack_rays produce) are
+// 16-byte aligned and are read as three 128-bit loads.
+// ------------------------------------------------------------------------------------------------
+struct RayRow {
+  float o[3], d[3], nr, fr, v[3];
+};
+__device__ __forceinline__ bool rays_vec4(const float* rays, int stride) {
+  return (stride & 3) == 0 && (reinterpret_cast<uintptr_t>(rays) & 15) == 0;
+}
+__device__ __forceinline__ RayRow load_ray(const float* __restrict__ rays, int stride, int64_t r) {
+  RayRow q;
+  const float* p = rays + r * stride;
+  if (rays_vec4(rays, stride)) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    const float4 c = __ldg(reinterpret_cast<const float4*>(p) + 2);
+    q.o[0] = a.x; q.o[1] = a.y; q.o[2] = a.z; q.d[0] = a.w; q.d[1] = b.x; q.d[2] = b.y;
+    q.nr = b.z; q.fr = b.w; q.v[0] = c.x; q.v[1] = c.y; q.v[2] = c.z;
+  } else {
+    q.o[0] = p[0]; q.o[1] = p[1]; q.o[2] = p[2]; q.d[0] = p[3]; q.d[1] = p[4]; q.d[2] = p[5];
+    q.nr = p[6]; q.fr = p[7]; q.v[0] = p[8]; q.v[1] = p[9]; q.v[2] = p[10];
+  }
+  return q;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Ray generation: get_rays (tools/run_nerf_helpers.py:153-168) + the packing of myRenderer.render
+// (models/render_class.py:158-179) in one kernel — the image's rays come from 21 scalars (K, c2w, near, far) passed by
+// value, so a frame needs no host->device input at all and a rank generates only its own ray range.
+// Operation order as torch evaluates it in fp32: dirs = [(i - cx) / fx, -(j - cy) / fy, -1];
+// rays_d[k] = (dirs0 * R[k][0] + dirs1 * R[k][1]) + dirs2 * R[k][2]; viewdir = rays_d / sqrt((d0^2 + d1^2) + d2^2).
+// Ray index = row * W + col (row-major, the "bit-exact ray indices" ordering).
+// ------------------------------------------------------------------------------------------------
+struct RayGen {
+  float cx, fx, cy, fy;
+  float R[9];
+  float o[3];
+  float nr, fr;
+  int W;
+};
+
+__global__ void generate_rays_kernel(const RayGen g, int64_t first, int64_t n, float* __restrict__ rays, int stride) {
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const int64_t r = first + idx;
+  const int row = static_cast<int>(r / g.W), col = static_cast<int>(r - static_cast<int64_t>(row) * g.W);
+  const float x = __fdiv_rn(__fsub_rn(static_cast<float>(col), g.cx), g.fx);
+  const float y = -__fdiv_rn(__fsub_rn(static_cast<float>(row), g.cy), g.fy);
+  float d[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+    d[k] = __fadd_rn(__fadd_rn(__fmul_rn(x, g.R[3 * k]), __fmul_rn(y, g.R[3 * k + 1])), -g.R[3 * k + 2]);
+  const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2])));
+  const float v0 = __fdiv_rn(d[0], nrm), v1 = __fdiv_rn(d[1], nrm), v2 = __fdiv_rn(d[2], nrm);
+  float* p = rays + idx * stride;
+  if (rays_vec4(rays, stride)) {
+    reinterpret_cast<float4*>(p)[0] = make_float4(g.o[0], g.o[1], g.o[2], d[0]);
+    reinterpret_cast<float4*>(p)[1] = make_float4(d[1], d[2], g.nr, g.fr);
+    reinterpret_cast<float4*>(p)[2] = make_float4(v0, v1, v2, 0.0f);
+  } else {
+    p[0] = g.o[0]; p[1] = g.o[1]; p[2] = g.o[2]; p[3] = d[0]; p[4] = d[1]; p[5] = d[2];
+    p[6] = g.nr; p[7] = g.fr; p[8] = v0; p[9] = v1; p[10] = v2;
+  }
+}
+
+cudaError_t launch_generate_rays(int H, int W, const float* K9, const float* c2w12, float nr, float fr, int64_t first,
+                                 int64_t n, float* rays, int stride, cudaStream_t s) {
+  (void)H;
+  if (n == 0) return cudaSuccess;
+  RayGen g;
+  g.fx = K9[0]; g.cx = K9[2]; g.fy = K9[4]; g.cy = K9[5];
+  for (int k = 0; k < 3; ++k) {
+    for (int j = 0; j < 3; ++j) g.R[3 * k + j] = c2w12[4 * k + j];
+    g.o[k] = c2w12[4 * k + 3];
+  }
+  g.nr = nr; g.fr = fr; g.W = W;
+  generate_rays_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(g, first, n, rays, stride);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
 // z_vals of the coarse pass
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float coarse_z(float nr, float fr, int i, int S, int lindisp) {
@@ -68,7 +150,13 @@ __global__ void zvals_coarse_kernel(const float* __restrict__ rays, int stride, 
   if (idx >= n * S) return;
   const int64_t r = idx / S;
   const int i = static_cast<int>(idx - r * S);
-  const float nr = rays[r * stride + 6], fr = rays[r * stride + 7];
+  float nr, fr;
+  if (rays_vec4(rays, stride)) {        // near / far sit in the second 16-byte word of a padded row
+    const float4 b = __ldg(reinterpret_cast<const float4*>(rays + r * stride) + 1);
+    nr = b.z; fr = b.w;
+  } else {
+    nr = rays[r * stride + 6]; fr = rays[r * stride + 7];
+  }
   float zi = coarse_z(nr, fr, i, S, lindisp);
   if (perturb > 0.0f) {
     const float zl = (i > 0) ? coarse_z(nr, fr, i - 1, S, lindisp) : zi;
@@ -149,14 +237,14 @@ __global__ void encode_rays_kernel(const float* __restrict__ rays, int stride, c
   const int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (p >= n * S) return;
   const int64_t r = p / S;
-  const float* ray = rays + r * stride;
+  const RayRow ray = load_ray(rays, stride, r);
   const float zi = z[p];
   // pts = rays_o + rays_d * z   (render_class.py:315,329): separate multiply and add, as torch does
-  const float px = __fadd_rn(ray[0], __fmul_rn(ray[3], zi));
-  const float py = __fadd_rn(ray[1], __fmul_rn(ray[4], zi));
-  const float pz = __fadd_rn(ray[2], __fmul_rn(ray[5], zi));
+  const float px = __fadd_rn(ray.o[0], __fmul_rn(ray.d[0], zi));
+  const float py = __fadd_rn(ray.o[1], __fmul_rn(ray.d[1], zi));
+  const float pz = __fadd_rn(ray.o[2], __fmul_rn(ray.d[2], zi));
   pe_row_f16<LX>(px, py, pz, X0 + p * 64, X0lo ? X0lo + p * 64 : nullptr);
-  if (V != nullptr) pe_row_f16<LV>(ray[8], ray[9], ray[10], V + p * 64);
+  if (V != nullptr) pe_row_f16<LV>(ray.v[0], ray.v[1], ray.v[2], V + p * 64);
 }
 
 template <int LX, int LV>

@@ -47,7 +47,12 @@ def render_sharded(render_fn: Callable[[torch.Tensor], Dict[str, torch.Tensor]],
         return render_fn(rays)
     n = rays.shape[0]
     lo, hi = shard_range(n, dist.get_rank(group), dist.get_world_size(group))
-    local = render_fn(rays[lo:hi])
+    return gather_ray_outputs(render_fn(rays[lo:hi]), n, lo, hi, group, max_floats_per_ray)
+
+
+def gather_ray_outputs(local: Dict[str, torch.Tensor], n: int, lo: int, hi: int, group=None,
+                       max_floats_per_ray: int = 32) -> Dict[str, torch.Tensor]:
+    """The collective half of render_sharded: `local` holds this rank's outputs for rays [lo, hi) of n."""
     keys = sorted(local.keys())
     widths = []
     for k in keys:

@@ -230,6 +230,23 @@ class Engine:
         self._keep["q"] = (p, v)
         return out.reshape(*shp, 4)
 
+    def generate_rays(self, H: int, W: int, K, c2w, near: float, far: float, first: int = 0,
+                      n: Optional[int] = None) -> torch.Tensor:
+        """get_rays + ray packing on the device (tools/run_nerf_helpers.py:153-168, models/render_class.py:158-179):
+        rows [first, first + n) of the row-major H x W ray batch as a [n, 12] tensor (o d near far viewdir pad).
+        K (3x3) and c2w ([3,4] or [4,4]) are read on the host: 21 scalars go to the kernel by value."""
+        total = int(H) * int(W)
+        n = total - first if n is None else int(n)
+        Kh = [float(K[a][b]) for a in range(3) for b in range(3)]
+        c = c2w.detach().cpu() if torch.is_tensor(c2w) else c2w
+        ch = [float(c[a][b]) for a in range(3) for b in range(4)]
+        out = torch.empty(n, 12, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.mofa_b200_generate_rays(self._h, int(H), int(W), (C.c_float * 9)(*Kh), (C.c_float * 12)(*ch),
+                                                        float(near), float(far), int(first), n, out.data_ptr(), 12,
+                                                        self._stream()))
+        return out
+
     # ------------------------------------------------------------------ op-level entry points
     def embed(self, x: torch.Tensor, multires: int) -> torch.Tensor:
         x = _f32c(x, self.device).reshape(-1, 3)

@@ -56,5 +56,7 @@ def pack_rays(rays_o, rays_d, near, far, viewdirs=None):
     far_t = far * torch.ones_like(rays_d[..., :1])
     rays = torch.cat([rays_o, rays_d, near_t, far_t], -1)
     if viewdirs is not None:
-        rays = torch.cat([rays, viewdirs], -1)
+        # 11 floats per ray in the reference; one zero column pads the row to 48 bytes so the kernels read it as
+        # three 128-bit loads (the engine accepts any row stride >= 11)
+        rays = torch.cat([rays, viewdirs, torch.zeros_like(near_t)], -1)
     return rays

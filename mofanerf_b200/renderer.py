@@ -79,6 +79,7 @@ class B200Renderer(torch.nn.Module):
         self.shard_rays = os.environ.get("MOFA_B200_SHARD", "0") == "1"
         self.seed = 0
         self._call = 0
+        self._local_range = None
 
     # ------------------------------------------------------------------ reference surface
     def grad_parameter(self):
@@ -212,7 +213,24 @@ class B200Renderer(torch.nn.Module):
                                gemm_simt=gemm_simt, **cfg)
 
     # ------------------------------------------------------------------ render / render_fitting
+    def _sharding(self):
+        return self.shard_rays and torch.distributed.is_available() and torch.distributed.is_initialized()
+
     def _rays_from_args(self, H, W, K, rays, c2w, ndc, near, far, use_viewdirs, c2w_staticcam):
+        """-> (ray batch [n, 12], output shape).  With a camera (c2w) and no gradient through it the rays come from
+        the engine's generate_rays kernel (nothing is uploaded, and under MOFA_B200_SHARD each rank
+        generates only its own range — recorded in self._local_range); otherwise from the PyTorch host path
+        (tools/run_nerf_helpers.py:153-199 semantics: explicit rays, NDC, c2w_staticcam, pose gradients)."""
+        self._local_range = None
+        if (c2w is not None and use_viewdirs and not ndc and c2w_staticcam is None and torch.cuda.is_available()
+                and not _needs_grad(c2w)):
+            n = int(H) * int(W)
+            lo, hi = 0, n
+            if self._sharding():
+                lo, hi = mdist.shard_range(n, torch.distributed.get_rank(), torch.distributed.get_world_size())
+                self._local_range = (lo, hi, n)
+            dev = c2w.device if torch.is_tensor(c2w) and c2w.device.type == "cuda" else None
+            return self.engine(dev).generate_rays(H, W, K, c2w, near, far, lo, hi - lo), (int(H), int(W), 3)
         if c2w is not None:
             rays_o, rays_d = get_rays(H, W, K, c2w)
         else:
@@ -247,20 +265,24 @@ class B200Renderer(torch.nn.Module):
         return rays
 
     def _render_all(self, chunk, sh, **kwargs):
-        if self.shard_rays and torch.distributed.is_available() and torch.distributed.is_initialized():
-            full = self.rays
-            if _needs_grad(full, self.shapeCodes, self.decoding_texCodes, self.expCodes_Sigma[self.expType]):
+        if self._sharding():
+            if _needs_grad(self.rays, self.shapeCodes, self.decoding_texCodes, self.expCodes_Sigma[self.expType]):
                 raise RuntimeError("MOFA_B200_SHARD=1 shards the rays of ONE image for inference; fitting / training need "
                                    "gradients: run them data-parallel (distributed.allreduce_gradients) instead")
+            if self._local_range is not None:      # the rays of this rank's range were generated in place
+                lo, hi, n = self._local_range
+                all_ret = mdist.gather_ray_outputs(self.batchify_rays(chunk, **kwargs), n, lo, hi)
+            else:
+                full = self.rays
 
-            def local_fn(r):
-                self.rays = r
-                return self.batchify_rays(chunk, **kwargs)
+                def local_fn(r):
+                    self.rays = r
+                    return self.batchify_rays(chunk, **kwargs)
 
-            try:
-                all_ret = mdist.render_sharded(local_fn, full)
-            finally:
-                self.rays = full
+                try:
+                    all_ret = mdist.render_sharded(local_fn, full)
+                finally:
+                    self.rays = full
         else:
             all_ret = self.batchify_rays(chunk, **kwargs)
         return self._finish(all_ret, sh)

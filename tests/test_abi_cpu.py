@@ -82,4 +82,5 @@ def test_host_ray_generation_matches_fixture():
     assert torch.equal(pose_spherical(30.0, 0.0, 16.0), torch.from_numpy(z["rays_c2w"]))
     vd = rd / torch.norm(rd, dim=-1, keepdim=True)
     rays = pack_rays(ro, rd, 8.0, 26.0, vd.reshape(-1, 3))
-    assert rays.shape == (60, 11) and float(rays[0, 6]) == 8.0 and float(rays[0, 7]) == 26.0
+    # 11 reference columns + one zero pad column (16-byte rows for 128-bit loads)
+    assert rays.shape == (60, 12) and float(rays[0, 6]) == 8.0 and float(rays[0, 7]) == 26.0 and float(rays[:, 11].abs().max()) == 0.0

@@ -1,0 +1,125 @@
+"""Round-2 GPU tests: in-kernel ray generation, the fine-net chain kernel against one launch per layer,
+padded 16-byte ray rows."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mofa_oracle as O
+from tests import parity_log
+from tests.helpers import GOLDEN, build_case_nets, load_case
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _ulps(a, b):
+    ai = a.contiguous().view(torch.int32).long()
+    bi = b.contiguous().view(torch.int32).long()
+    return (ai - bi).abs().max().item()
+
+
+def test_generate_rays_matches_get_rays_bit_exact():
+    """mofa_b200_generate_rays against tools/run_nerf_helpers.py:153-168 (fixture from the unmodified reference for a
+    6x10 camera, and the oracle's restatement — itself pinned to that fixture — for the 800x800 frame of the bench):
+    origins and directions bit for bit, row-major ray order, near / far columns, unit view directions; any sub-range
+    (what a rank of a ray-sharded render generates) equals the same rows of the full batch."""
+    from mofanerf_b200 import get_engine
+    eng = get_engine(DEV)
+    z = np.load(os.path.join(GOLDEN, "ops.npz"))
+    K, c2w = z["rays_K"], torch.from_numpy(z["rays_c2w"])
+    rays = eng.generate_rays(6, 10, K, c2w[:3, :4], 8.0, 26.0).cpu()
+    assert rays.shape == (60, 12)
+    assert torch.equal(rays[:, 0:3], torch.from_numpy(z["rays_o"]).reshape(-1, 3))
+    assert torch.equal(rays[:, 3:6], torch.from_numpy(z["rays_d"]).reshape(-1, 3))
+    H = W = 800
+    focal = 1200.0 * H / 512.0
+    K = np.array([[focal, 0, 0.5 * W], [0, focal, 0.5 * H], [0, 0, 1]])
+    worst = 0
+    for angle in (30.0, -110.0):
+        c2w = O.pose_spherical(angle, 0.0, 16.0)
+        ro, rd = O.get_rays(H, W, K, c2w[:3, :4])
+        ref = O.make_ray_batch(ro, rd, 8.0, 26.0)
+        got = eng.generate_rays(H, W, K, c2w[:3, :4].to(DEV), 8.0, 26.0).cpu()
+        assert got.shape == (H * W, 12) and float(got[:, 11].abs().max()) == 0.0
+        assert torch.equal(got[:, 0:8], ref[:, 0:8]), "origins / directions / near / far differ from get_rays"
+        u = _ulps(got[:, 8:11], ref[:, 8:11])
+        worst = max(worst, u)
+        assert u <= 1, f"view directions differ from rays_d / torch.norm(rays_d) by {u} ulp"
+        sub = eng.generate_rays(H, W, K, c2w[:3, :4], 8.0, 26.0, first=123457, n=1001).cpu()
+        assert torch.equal(sub, got[123457:123457 + 1001])
+    parity_log.record("generate_rays 800x800", rays_od_max_ulp=0, viewdir_max_ulp=worst)
+    with pytest.raises(RuntimeError, match="outside"):
+        eng.generate_rays(4, 4, K, c2w[:3, :4], 8.0, 26.0, first=10, n=10)
+
+
+def test_render_from_camera_equals_render_from_rays():
+    """render_fitting(c2w=...) (rays generated on the device, 12-float rows) against render_fitting(rays=...) with the
+    host-generated rays of the same camera, and 11-float rows against padded rows: same image."""
+    from mofanerf_b200 import B200Renderer
+    meta, inp, _ = load_case("full_w1024")
+    c, f, s = build_case_nets(meta)
+    r = B200Renderer(expCodesLen=30).to(DEV)
+    r.idSpecificMod.load_state_dict(s.state_dict())
+    H, W = 12, 10
+    focal = 1200.0 * H / 512.0
+    K = np.array([[focal, 0, 0.5 * W], [0, focal, 0.5 * H], [0, 0, 1]])
+    c2w = O.pose_spherical(25.0, 0.0, 16.0)
+    kw = dict(shapeCodes=inp["shape"].to(DEV), uvCodes=inp["tex"].to(DEV), expType=20, expCodes=inp["exp"].to(DEV), near=8.0,
+              far=26.0, use_viewdirs=True, ndc=False, network_fn=c.to(DEV), network_fine=f.to(DEV), N_samples=64,
+              N_importance=64, perturb=0.0, raw_noise_std=0.0)
+    ro, rd = O.get_rays(H, W, K, c2w[:3, :4])
+    with torch.no_grad():
+        a = r.render_fitting(H, W, K, c2w=c2w[:3, :4].to(DEV), **kw)
+        b = r.render_fitting(H, W, K, rays=(ro.to(DEV), rd.to(DEV)), **kw)
+    assert a[0].shape == (H, W, 3) and b[0].shape == (H, W, 3)
+    d = (a[0] - b[0]).abs().max().item()
+    parity_log.record("render(c2w) vs render(rays)", rgb_map_max=d)
+    assert d <= 2e-3, f"camera path vs ray path: {d:.2e}"      # view directions may differ by 1 ulp before fp16 rounding
+    eng = r.engine(DEV)
+    rays12 = eng.generate_rays(H, W, K, c2w[:3, :4], 8.0, 26.0)
+    rays11 = rays12[:, :11].contiguous()
+    o12 = eng.render_rays(rays12, 64, 64)
+    o11 = eng.render_rays(rays11, 64, 64)
+    assert torch.equal(o12["rgb_map"], o11["rgb_map"]) and torch.equal(o12["z_std"], o11["z_std"])
+
+
+def test_fine_chain_kernel_equals_per_layer_launches():
+    """The persistent chain kernel (all 25 dense layers of the W = 1024 net in one launch, L2-resident activation
+    slabs) runs the same tiles with the same arithmetic as one launch per layer: every output bit for bit, for ray
+    counts below, at and above a slab (74 rays at 128 samples) and not multiples of a tile."""
+    from mofanerf_b200 import nets
+    from mofanerf_b200.engine import Engine
+    coarse, fine, _ = nets.build_nets(0, device=DEV)
+    g = torch.Generator().manual_seed(3)
+    shape, tex, em = torch.randn(50, generator=g) * 0.034, 0.14 + 0.26 * torch.randn(256, generator=g), torch.rand(30, generator=g)
+
+    def rays_for(n):
+        gg = torch.Generator().manual_seed(n)
+        rd = torch.nn.functional.normalize(torch.randn(n, 3, generator=gg) * 0.1 + torch.tensor([0.0, 0.0, -1.0]), dim=-1)
+        ro = torch.zeros(n, 3) + torch.tensor([0.0, 0.0, 16.0])
+        return torch.cat([ro, rd, torch.full((n, 1), 8.0), torch.full((n, 1), 26.0), rd, torch.zeros(n, 1)], -1).to(DEV)
+
+    outs = {}
+    for mode in ("chain", "per_layer"):
+        if mode == "per_layer":
+            os.environ["MOFA_B200_FINE_PER_LAYER"] = "1"
+        try:
+            eng = Engine(DEV)
+        finally:
+            os.environ.pop("MOFA_B200_FINE_PER_LAYER", None)
+        eng.load_network(0, coarse)
+        eng.load_network(1, fine)
+        eng.set_latents(shape, em, tex)
+        for n, S, Ni in ((3, 64, 64), (74, 64, 64), (233, 64, 64), (41, 32, 16)):
+            o = eng.render_rays(rays_for(n), S, Ni, retraw=True)
+            torch.cuda.synchronize()
+            outs[(mode, n)] = {k: v.clone() for k, v in o.items()}
+        eng.close()
+    for (mode, n), o in outs.items():
+        if mode != "chain":
+            continue
+        ref = outs[("per_layer", n)]
+        for k in o:
+            assert torch.allclose(o[k], ref[k], rtol=0, atol=0, equal_nan=True), f"n={n} {k}: chain kernel differs from per-layer launches"

@@ -26,7 +26,8 @@ def rays_for(n):
 
 
 res = {}
-for mode in ("chain", "per_layer"):
+MODES = os.environ.get("MODES", "chain,per_layer").split(",")
+for mode in MODES:
     if mode == "per_layer":
         os.environ["MOFA_B200_FINE_PER_LAYER"] = "1"
     eng = Engine(DEV)
@@ -34,7 +35,7 @@ for mode in ("chain", "per_layer"):
     eng.load_network(0, coarse)
     eng.load_network(1, fine)
     eng.set_latents(shape, em, tex)
-    for n in (5, 75, 300, 1061):
+    for n in ((5, 75, 300, 1061) if len(MODES) == 2 else ()):
         out = eng.render_rays(rays_for(n), 64, 64, retraw=True)
         torch.cuda.synchronize()
         res[(mode, n)] = {k: v.clone() for k, v in out.items()}
@@ -49,7 +50,7 @@ for mode in ("chain", "per_layer"):
         dt = time.perf_counter() - t0
     print(f"[{mode}] {n} rays: {dt * 1e3:.2f} ms -> {n / dt:.0f} rays/s", flush=True)
     eng.close()
-for n in (5, 75, 300, 1061):
+for n in ((5, 75, 300, 1061) if len(MODES) == 2 else ()):
     a, b = res[("chain", n)], res[("per_layer", n)]
     same = {k: bool(torch.equal(a[k], b[k])) or bool(torch.allclose(a[k], b[k], equal_nan=True, atol=0, rtol=0)) for k in a}
     worst = max((a[k] - b[k]).abs().max().item() for k in ("rgb_map", "raw"))
