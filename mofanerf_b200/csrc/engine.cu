@@ -137,14 +137,17 @@ namespace {
 
 using namespace mofa;
 
+// box_cols = 64 (128-byte rows, SWIZZLE_128B: every operand load and the per-layer kernels' stores) or 32 (64-byte rows,
+// SWIZZLE_64B: the chain kernel's half-block stores)
 int make_tmap_2d(mofa_b200_ctx* c, CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t pitch,
-                 uint32_t box_rows) {
+                 uint32_t box_rows, uint32_t box_cols = 64) {
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {pitch * sizeof(__half)};
-  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = c->encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail("cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu pitch=%llu box_rows=%u ptr=%p", (int)r,
@@ -374,6 +377,17 @@ struct ViewSrc {
 };
 
 constexpr int kChainMaxLayers = 40;
+
+// m-blocks per slab of the fine-net chain kernel (default kChainSlabMb = 56: three rounds of the 74 pairs per layer,
+// 3 x 29 MB of activations); MOFA_B200_CHAIN_SLAB overrides it for measurements
+int chain_slab_mb() {
+  static const int v = [] {
+    const char* e = getenv("MOFA_B200_CHAIN_SLAB");
+    const int n = e ? atoi(e) : 0;
+    return (n >= 8 && n <= 1024) ? n : kChainSlabMb;
+  }();
+  return v;
+}
 constexpr int64_t kSmallRows = 65536;     // activation-buffer rows kept for the per-layer / SIMT paths when the chain kernel is on
 
 // Rows of the three rotating activation buffers.  With the chain kernel the fine net only ever touches one slab of them
@@ -389,7 +403,7 @@ int64_t t_rows_for(const mofa_b200_ctx* c, int64_t P_pad) {
       if (c->nets[i].W % 512 != 0 || c->nets[i].W > 1024) chain = false;
     }
   if (!chain || !any) return P_pad;
-  const int64_t slab = static_cast<int64_t>(kChainSlabMb) * 256;
+  const int64_t slab = static_cast<int64_t>(chain_slab_mb()) * 256;
   const int64_t small = P_pad < kSmallRows ? P_pad : kSmallRows;
   return small > slab ? small : slab;
 }
@@ -441,7 +455,7 @@ bool chain_applies(const mofa_b200_ctx* c, const Net& net) {
 
 int run_chain(mofa_b200_ctx* c, Net& net, const Workspace& ws, int64_t P_rows, cudaStream_t s) {
   const int net_id = static_cast<int>(&net - c->nets);
-  const int64_t slab_rows = static_cast<int64_t>(kChainSlabMb) * 256;
+  const int64_t slab_rows = static_cast<int64_t>(chain_slab_mb()) * 256;
   if (ws.t_rows < slab_rows) return fail("chain kernel: activation buffers have %lld rows, need %lld", (long long)ws.t_rows, (long long)slab_rows);
   const void* key[4] = {ws.T[0], ws.X0, ws.V, &net};
   if (c->chain_maps == nullptr) {
@@ -497,7 +511,8 @@ int run_chain(mofa_b200_ctx* c, Net& net, const Workspace& ws, int64_t P_rows, c
       }
       {
         CUtensorMap m;
-        if (make_tmap_2d(c, &m, ws.T[st.out - SRC_T0], (uint64_t)slab_rows, (uint64_t)L.N, (uint64_t)L.N, 128)) return 1;
+        // output map: 32-column boxes (the epilogue stages and stores half a 64-column block at a time, double-buffered)
+        if (make_tmap_2d(c, &m, ws.T[st.out - SRC_T0], (uint64_t)slab_rows, (uint64_t)L.N, (uint64_t)L.N, 128, 32)) return 1;
         maps.push_back(m);
         d.mapC = static_cast<int>(maps.size()) - 1;
       }
@@ -523,8 +538,12 @@ int run_chain(mofa_b200_ctx* c, Net& net, const Workspace& ws, int64_t P_rows, c
     P.nt = nt;
     P.nt_last = nt_last;
     P.tiles_per_mb = tiles_per_mb;
-    P.slab_mb = kChainSlabMb;
+    P.slab_mb = chain_slab_mb();
     P.head_stride = kHeadStride;
+    {
+      const char* v = getenv("MOFA_B200_CHAIN_NODEP");
+      P.nodep = (v && v[0] == '1') ? 1 : 0;
+    }
   }
   ChainParams P = c->chain_proto;
   P.total_mb = static_cast<int>((P_rows + 255) / 256);

@@ -169,10 +169,12 @@ struct ChainParams {
   int head_stride;
   int64_t P_rows;
   uint32_t* counters;                     // [n_layers, total_mb], zero before the launch
+  int nodep;                              // MEASUREMENT ONLY (MOFA_B200_CHAIN_NODEP=1): skip the dependency waits (wrong results)
 };
 cudaError_t launch_fine_chain(const ChainParams& p, int num_sms, cudaStream_t stream);
 cudaError_t fine_chain_configure();
-constexpr int kChainSlabMb = 37;          // 37 m-blocks x 4 n-tiles = two rounds of the 74 CTA pairs per layer
+constexpr int kChainSlabMb = 56;          // m-blocks per slab: 56 x 4 n-tiles = three rounds of the 74 CTA pairs per layer
+                                          // (measured 37 / 56 / 74 / 111: 162.2 / 168.6 / 166.1 / 157.6 k rays/s on one box)
 
 // ---- backward pass (backward.cu) ----------------------------------------------------------------
 cudaError_t launch_composite_bwd(const float* raw, const float* z, const float* rays, int stride, const float* noise,

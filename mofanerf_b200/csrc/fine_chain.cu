@@ -6,18 +6,22 @@
 // GPU sits at its 1 kW power cap and every HBM byte is paid for in SM clock (round-1 verdict: 0.80 pJ/FLOP against cuBLAS's
 // 0.73).  The only traffic the algorithm needs is 365 KB of rays per chunk.
 //
-// How: the point rows are processed in SLABS of 37 m-blocks (9472 rows = 74 rays x 128 samples).  For one slab the
-// three rotating activation buffers are 3 x 19.4 MB — together with the weights they fit the 126 MB L2 — and every slab
-// re-uses the SAME physical buffers, so activations are written and read back through L2 without ever having to reach
-// HBM.  Work item = (slab, layer, m-block, n-tile) = one 256 x 256 output tile of one layer; items are numbered slab-major,
-// then layer, then m-block, then n-tile, and pair p takes items p, p + 74, p + 148, ... — a layer of a full slab is
-// exactly two rounds of the 74 pairs.  A tile of layer l needs the four n-tiles of layer l-1 of ITS m-block only, which
-// lie two rounds back in that order: by the time a pair's producer warp polls the m-block's completion counter
-// (ld.acquire.gpu) it is almost always already there.  Counters are bumped by the epilogue (red.release.gpu) after the
-// tile's TMA stores have completed (cp.async.bulk.wait_group 0) and a proxy fence; the consumer fences the async proxy
-// again before its TMA loads.  Layer 0 of slab s waits for the last layer of slab s-1 at the same local m-block (the
-// buffers it overwrites are free then).  Every dependency points to a lower item number and all 74 pairs are co-resident,
-// so the pair holding the lowest unfinished item can always run: no deadlock.
+// How: the point rows are processed in SLABS of 56 m-blocks (14336 rows = 112 rays x 128 samples).  For one slab the
+// three rotating activation buffers are 3 x 29 MB — together with the layer's weights they stay inside the 126 MB L2 —
+// and every slab re-uses the SAME physical buffers, so activations are written and read back through L2 and only a
+// small remainder reaches HBM (ncu, whole 25-layer pass over 4144 rays: 8.2 GB of DRAM traffic instead of 53 GB).
+// Work item = (slab, layer, m-block, n-tile) = one 256 x 256 output tile of one layer; items are numbered slab-major,
+// then layer, then m-block, then n-tile, and pair p takes items p, p + 74, p + 148, ... — a layer of a full slab is about
+// three rounds of the 74 pairs.  A tile of layer l needs the four n-tiles of layer l-1 of ITS m-block only, which lie
+// three rounds back in that order: by the time a pair's producer warp polls the m-block's completion counter it is
+// almost always already there (skipping the waits altogether changes the frame time by ~1 %).  Counters are bumped by
+// the epilogue (red.release.gpu) after the tile's TMA stores have completed (cp.async.bulk.wait_group 0) and a proxy
+// fence; the consumer fences the async proxy again before its TMA loads.  Layer 0 of slab s waits for the last layer of
+// slab s-1 at the same local m-block (the buffers it overwrites are free then).  Every dependency points to a lower item
+// number and all 74 pairs are co-resident, so the pair holding the lowest unfinished item can always run: no deadlock.
+// Slab size is a trade: fewer m-blocks = fewer rounds between a tile and its dependencies (stalls), more = activations
+// that no longer fit L2 (HBM traffic, i.e. power and clock): 37 / 56 / 74 / 111 m-blocks measured 162.2 / 168.6 / 166.1 /
+// 157.6 k rays/s on one box (one launch per layer: 157-165 k).
 //
 // The tile pipeline itself is the CTA-pair kernel of dense_tc2.cu (cta_group::2 UMMA 256x256x16, 6-stage TMA ring,
 // double-buffered TMEM accumulators, 8 epilogue warps, fused alpha / rgb heads); what changes per tile are the tensor
@@ -41,9 +45,23 @@ struct ChainSmem {
   static constexpr int OFF_BAR = OFF_C + 2 * C_BYTES;            // one staging buffer per epilogue group
   static constexpr int N_BARS = 2 * kChainStages + 4;
   static constexpr int OFF_TPTR = OFF_BAR + N_BARS * 8;
-  static constexpr int TOTAL = OFF_TPTR + 16;
+  static constexpr int OFF_LAYERS = OFF_TPTR + 16;              // compact per-layer table (40 bytes x kChainMaxLayersSm)
+  static constexpr int TOTAL = OFF_LAYERS + 40 * 40;
   static constexpr int DYN_BYTES = TOTAL + 1024;
 };
+static_assert(ChainSmem::DYN_BYTES <= 232448, "chain kernel exceeds the 227 KB shared-memory limit");
+
+// What the three roles need per tile, kept in shared memory: fetched from global memory per tile it cost every role an
+// L2 round trip at each tile start (the SM's L1 is invalidated twice per tile, see chain_epilogue) — for the MMA issuer
+// that is tensor-pipe idle time.
+struct ChainLayerSm {
+  const float* bias;
+  const float* head_w;
+  uint16_t mapA0, mapA1, mapB0, mapB1, mapC, N;
+  uint8_t kb0, kb1, a0_global, a1_global, relu, store_c, head_n, head_slot0;
+  uint8_t pad[4];
+};
+static_assert(sizeof(ChainLayerSm) == 40, "ChainLayerSm layout");
 
 struct ChainTile {
   int layer, mb_local, mb_global, n;
@@ -122,11 +140,10 @@ __device__ __forceinline__ void chain_epilogue(const EpiParams& p, const void* t
   for (int q = 0; q < 4; ++q) {
     const int cb = g.cb0 + (q >> 1), h = q & 1;
     const int ncol = col_base + q * 32;
-    const uint32_t cbuf = g.cbuf0;
-    if (h == 0 && p.store_c) {
-      if (g.gtid == 0) tma_store_wait_read<0>();           // the store that last read the staging buffer is done
-      named_bar_sync(g.bar_id, 128);
-    }
+    (void)h;
+    // staging: two 8 KB half-buffers per group (32 columns x 128 rows, 64-byte rows, SWIZZLE_64B), alternating per chunk,
+    // so the TMA store of chunk q reads its buffer while chunk q + 1 is computed into the other one
+    const uint32_t cbuf = g.cbuf0 + (q & 1) * (128 * 32 * 2);
     uint32_t v[32];
     tmem_ld_32x32b_x32(acc_addr + cb * 64 + h * 32, v);
     constexpr int HB = (HEAD == 3) ? 1 : 4;           // 8-column blocks of head weights per fetch
@@ -187,19 +204,22 @@ __device__ __forceinline__ void chain_epilogue(const EpiParams& p, const void* t
         __half2 h1 = __floats2half2_rn(f[2], f[3]);
         __half2 h2 = __floats2half2_rn(f[4], f[5]);
         __half2 h3 = __floats2half2_rn(f[6], f[7]);
-        const int chunk = h * 4 + j;              // 16-byte chunk within the 128-byte row
-        const uint32_t addr = cbuf + row * 128 + ((chunk ^ (row & 7)) << 4);
+        // 64-byte swizzle: 16-byte chunk index (2 bits) xor address bits [7,9) = (row >> 1) & 3
+        const uint32_t addr = cbuf + row * 64 + ((j ^ ((row >> 1) & 3)) << 4);
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
                      "r"(*reinterpret_cast<uint32_t*>(&h0)), "r"(*reinterpret_cast<uint32_t*>(&h1)),
                      "r"(*reinterpret_cast<uint32_t*>(&h2)), "r"(*reinterpret_cast<uint32_t*>(&h3))
                      : "memory");
       }
     }
-    if (h == 1 && p.store_c) {
+    if (p.store_c) {
       fence_proxy_async_smem();
+      // one barrier per chunk: before it, thread 0 makes sure the store of chunk q - 1 has finished READING its buffer —
+      // the buffer chunk q + 1 will be written into — so that nobody has to wait for a store that was only just issued
+      if (g.gtid == 0) tma_store_wait_read<0>();
       named_bar_sync(g.bar_id, 128);
       if (g.gtid == 0) {
-        tma_store_2d(tmC, cbuf, n0 + cb * 64, m0);
+        tma_store_2d(tmC, cbuf, ncol, m0);
         tma_store_commit();
       }
     }
@@ -248,6 +268,19 @@ fine_chain_kernel(const ChainParams p) {
     }
     fence_mbar_init();
   }
+  {
+    ChainLayerSm* lt = reinterpret_cast<ChainLayerSm*>(base_ptr + L::OFF_LAYERS);
+    for (int i = threadIdx.x; i < p.n_layers; i += blockDim.x) {
+      const ChainLayerDesc d = p.layers[i];
+      ChainLayerSm q;
+      q.bias = d.bias; q.head_w = d.head_w;
+      q.mapA0 = d.mapA0; q.mapA1 = d.mapA1; q.mapB0 = d.mapB0; q.mapB1 = d.mapB1; q.mapC = d.mapC; q.N = d.N;
+      q.kb0 = d.kb0; q.kb1 = d.kb1; q.a0_global = d.a0_global; q.a1_global = d.a1_global; q.relu = d.relu;
+      q.store_c = d.store_c; q.head_n = d.head_n; q.head_slot0 = d.head_slot0;
+      q.pad[0] = q.pad[1] = q.pad[2] = q.pad[3] = 0;
+      lt[i] = q;
+    }
+  }
   __syncthreads();
   cluster_sync_all();
   if (warp == 2) {
@@ -259,6 +292,7 @@ fine_chain_kernel(const ChainParams p) {
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(base_ptr + L::OFF_TPTR);
 
+  ChainLayerSm* lsm = reinterpret_cast<ChainLayerSm*>(base_ptr + L::OFF_LAYERS);
   const long long num_items = static_cast<long long>(p.total_mb) * p.tiles_per_mb;
   const int pair = blockIdx.x >> 1;
   const int num_pairs = gridDim.x >> 1;
@@ -271,10 +305,10 @@ fine_chain_kernel(const ChainParams p) {
       uint32_t phase = 0;
       for (long long t = pair; t < num_items; t += num_pairs) {
         const ChainTile c = chain_decode(p, t);
-        const ChainLayerDesc d = p.layers[c.layer];
+        const ChainLayerSm d = lsm[c.layer];
         // dependency: the previous layer's n-tiles of this m-block (or, for layer 0 of a later slab, the last layer of
         // the previous slab at the same local m-block: the activation buffers it still reads are overwritten from here on)
-        if (lane == 0) {
+        if (lane == 0 && !p.nodep) {
           if (c.layer > 0) {
             wait_counter(p.counters + static_cast<size_t>(c.layer - 1) * p.total_mb + c.mb_global, 4u * p.nt);
           } else if (c.mb_global >= p.slab_mb) {
@@ -322,8 +356,7 @@ fine_chain_kernel(const ChainParams p) {
       int it = 0;
       for (long long t = pair; t < num_items; t += num_pairs, ++it) {
         const ChainTile c = chain_decode(p, t);
-        const ChainLayerDesc d = p.layers[c.layer];
-        const int total_kb = d.kb0 + d.kb1;
+        const int total_kb = lsm[c.layer].kb0 + lsm[c.layer].kb1;
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
         mbar_wait(tempty0 + 8 * as, aphase ^ 1u);
@@ -365,7 +398,7 @@ fine_chain_kernel(const ChainParams p) {
     int it = 0;
     for (long long t = pair; t < num_items; t += num_pairs, ++it) {
       const ChainTile c = chain_decode(p, t);
-      const ChainLayerDesc d = p.layers[c.layer];
+      const ChainLayerSm d = lsm[c.layer];
       EpiParams e;
       e.bias = d.bias;
       e.head_w = d.head_w;

@@ -103,8 +103,10 @@ __global__ void generate_rays_kernel(const RayGen g, int64_t first, int64_t n, f
   float d[3];
 #pragma unroll
   for (int k = 0; k < 3; ++k)
-    d[k] = __fadd_rn(__fadd_rn(__fmul_rn(x, g.R[3 * k]), __fmul_rn(y, g.R[3 * k + 1])), -g.R[3 * k + 2]);
-  const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2])));
+    // torch.sum starts from +0: (0 + a) turns a = -0 into +0, which matters for the sign of exact zeros
+    d[k] = __fadd_rn(__fadd_rn(__fadd_rn(0.0f, __fmul_rn(x, g.R[3 * k])), __fmul_rn(y, g.R[3 * k + 1])), -g.R[3 * k + 2]);
+  // torch.norm's reduction is acc + x * x compiled with contraction: two fused multiply-adds after the first square
+  const float nrm = sqrtf(__fmaf_rn(d[2], d[2], __fmaf_rn(d[1], d[1], __fmul_rn(d[0], d[0]))));
   const float v0 = __fdiv_rn(d[0], nrm), v1 = __fdiv_rn(d[1], nrm), v2 = __fdiv_rn(d[2], nrm);
   float* p = rays + idx * stride;
   if (rays_vec4(rays, stride)) {

@@ -155,7 +155,12 @@ def test_config2_400x400_full_frame_properties():
         from mofanerf_b200.rays import get_rays
         ro, rd = get_rays(H, W, K, c2w[:3, :4].to(DEV))
         idx = torch.linspace(0, H * W - 1, 97).long().to(DEV)
-        sub = r.render_fitting(1, 97, None, rays=(ro.reshape(-1, 3)[idx], rd.reshape(-1, 3)[idx]), **args, **_kw(c, f))[0]
+        # the frame's rays come from the engine's generate_rays kernel; render the SAME ray rows on their own
+        eng = r.engine(DEV)
+        all_rays = eng.generate_rays(H, W, K, c2w[:3, :4], 8.0, 26.0)
+        rd_cpu = get_rays(H, W, K, c2w[:3, :4])[1]       # torch on the CPU (the fixtures' arithmetic), not torch's CUDA reduction
+        assert torch.equal(all_rays[:, 3:6].cpu(), rd_cpu.reshape(-1, 3)), "generate_rays vs get_rays"
+        sub = eng.render_rays(all_rays[idx], 64, 64)["rgb_map"]
         assert torch.equal(sub, rgb.reshape(-1, 3)[idx]), "row-major ray index / per-ray independence"
         ref_rays = O.make_ray_batch(ro.reshape(-1, 3)[idx[:12]].cpu(), rd.reshape(-1, 3)[idx[:12]].cpu(), 8.0, 26.0)
         ref = O.render_rays(ref_rays, c.cpu(), f.cpu(), inp["shape"], O.expression_mod(s, inp["shape"], inp["exp"]), inp["tex"])

@@ -15,9 +15,10 @@ DEV = "cuda:0"
 
 
 def _ulps(a, b):
-    ai = a.contiguous().view(torch.int32).long()
-    bi = b.contiguous().view(torch.int32).long()
-    return (ai - bi).abs().max().item()
+    def ordered(x):      # monotone integer image of the floats (negative values mirrored), so differences count ulps
+        i = x.contiguous().view(torch.int32).long()
+        return torch.where(i < 0, -(i & 0x7FFFFFFF), i)
+    return (ordered(a) - ordered(b)).abs().max().item()
 
 
 def test_generate_rays_matches_get_rays_bit_exact():
@@ -44,6 +45,7 @@ def test_generate_rays_matches_get_rays_bit_exact():
         got = eng.generate_rays(H, W, K, c2w[:3, :4].to(DEV), 8.0, 26.0).cpu()
         assert got.shape == (H * W, 12) and float(got[:, 11].abs().max()) == 0.0
         assert torch.equal(got[:, 0:8], ref[:, 0:8]), "origins / directions / near / far differ from get_rays"
+        assert _ulps(got[:, 0:8], ref[:, 0:8]) == 0, "signed zeros differ from get_rays"
         u = _ulps(got[:, 8:11], ref[:, 8:11])
         worst = max(worst, u)
         assert u <= 1, f"view directions differ from rays_d / torch.norm(rays_d) by {u} ulp"
