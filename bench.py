@@ -53,8 +53,13 @@ def parse():
                     help="skip timing the reference algorithm (fp32 / TF32 PyTorch eager port) on this GPU — the denominator "
                          "of the north_star's '>=10x the reference single-GPU PyTorch path' (part of the default N=1 line)")
     ap.add_argument("--torch-gpu-baseline", action="store_true", help=argparse.SUPPRESS)   # round-1 flag, now the default
-    ap.add_argument("--workload", default="frame", choices=["frame", "fit", "train"],
-                    help="frame: BASELINE metric (800x800 FULL render); fit: run_fit.py iteration (1024 rays, fwd+bwd+Adam)")
+    ap.add_argument("--workload", default="frame", choices=["frame", "fit", "train", "sweep20", "ids300"],
+                    help="frame: BASELINE metric (800x800 FULL render); fit: run_fit.py iteration (1024 rays, fwd+bwd+Adam); "
+                         "sweep20: BASELINE config #4 (20 expression slots, 800x800, render_fitting per image); "
+                         "ids300: BASELINE config #5 (identities x 4 views through render_path -> render -> texEncoder, 256x256)")
+    ap.add_argument("--images", type=int, default=0,
+                    help="images per step of the sweep20 / ids300 workloads (0 = 20 for sweep20, 48 for ids300; the full "
+                         "config #5 batch is 1200)")
     return ap.parse_args()
 
 
@@ -349,6 +354,188 @@ def run_fit_workload(args, train=False):
                       "config": {"workload": ("run_train.py step" if train else "BASELINE config #3: fitting loop") + ", N_rand=1024, FULL, 1 x B200"}}), flush=True)
 
 
+def run_image_workload(args, rank, world, local_rank):
+    """BASELINE configs #4 and #5: many images, each with its own latents, rays sharded across the ranks inside every
+    image (contiguous row-major ranges generated on the device from the camera) and ONE all-gather per image.
+    One step = all images of the batch.  `value` = rays/s with the per-image inputs (camera, codes / UV maps) already on
+    the device and the frames left on the device; `e2e` = the same batch through the reference-facing calls with host
+    inputs, device->host copies and PNG files written (AsyncImageSink / render_path), i.e. what run_fit.py:394-403 and
+    render_refine_trainSet.py:245-304 do per image."""
+    import tempfile
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    import __graft_entry__
+    __graft_entry__.build()
+    from mofanerf_b200 import B200Renderer, nets
+    from mofanerf_b200.rays import pose_spherical
+    from mofanerf_b200.renderer import AsyncImageSink
+
+    sweep = args.workload == "sweep20"
+    H = W = (args.H if sweep else 256)
+    n_img = args.images if args.images > 0 else (20 if sweep else 48)
+    coarse, fine, style = nets.build_nets(0, device=dev)
+    torch.manual_seed(7)
+    r = B200Renderer(expCodesLen=30).to(dev)
+    r.idSpecificMod.load_state_dict(style.state_dict())
+    r.shard_rays = world > 1
+    focal = 1200.0 * H / 512.0
+    K = np.array([[focal, 0, 0.5 * W], [0, focal, 0.5 * H], [0, 0, 1]])
+    kw = dict(near=8.0, far=26.0, use_viewdirs=True, ndc=False, network_fn=coarse, network_fine=fine,
+              N_samples=args.n_samples, N_importance=args.n_importance, perturb=0.0, raw_noise_std=0.0)
+    g = torch.Generator().manual_seed(11)
+    if sweep:      # one identity, 20 expression slots, one camera (run_fit.py:384,394)
+        shape = (torch.randn(1, 50, generator=g) * 0.034).to(dev)
+        tex = (0.14 + 0.26 * torch.randn(256, generator=g)).to(dev)
+        pose = pose_spherical(0.0, 0.0, 16.0)[:3, :4]
+        slots = [i % 20 for i in range(n_img)]
+    else:          # identities x 4 views: own shape code, own UV map, own expression slot, own pose
+        n_id = (n_img + 3) // 4
+        shapes_h = torch.randn(n_id, 50, generator=g) * 0.034
+        uv_h = torch.rand(min(n_id, 8), 512, 512, 3, generator=g).pin_memory()      # 8 distinct maps, cycled (3 MB each)
+        poses_h = torch.stack([pose_spherical(-60.0 + 40.0 * (i % 4), 0.0, 16.0) for i in range(n_img)])
+        exp_slots = [int(x) for x in torch.randint(0, 20, (n_img,), generator=g)]
+        shapes_img = shapes_h[torch.arange(n_img) // 4]
+        uv_idx = [int(x) for x in (torch.arange(n_img) // 4) % uv_h.shape[0]]
+        uv_d, sh_d = uv_h.to(dev), shapes_img.to(dev)          # device-resident inputs of the `value` arm
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def step_device():
+        outs = None
+        with torch.no_grad():
+            if sweep:
+                for e in slots:
+                    outs = r.render_fitting(H, W, K, chunk=1 << 30, c2w=pose, shapeCodes=shape, uvCodes=tex, expType=20,
+                                            expCodes=r.expCodes_Sigma[e], **kw)[0]
+            else:
+                for i in range(n_img):
+                    outs = r.render(H, W, K, chunk=1 << 30, c2w=poses_h[i][:3, :4], shapeCodes=sh_d[i].reshape(1, -1),
+                                    uvMap=uv_d[uv_idx[i]], expType=exp_slots[i], **kw)[0]
+        return outs
+
+    png_bytes = [0]
+
+    def step_e2e():
+        with tempfile.TemporaryDirectory() as tmp, torch.no_grad():
+            if sweep:
+                sink = AsyncImageSink()
+                for k, e in enumerate(slots):
+                    rgb = r.render_fitting(H, W, K, chunk=1 << 30, c2w=pose, shapeCodes=shape, uvCodes=tex, expType=20,
+                                           expCodes=r.expCodes_Sigma[e], **kw)[0]
+                    sink.submit([rgb], os.path.join(tmp, f"rigging_{k:03d}.png") if rank == 0 else None)
+                sink.results()
+                sink.close()
+                png_bytes[0] = sink.png_bytes
+            else:     # render_path per image, exactly as render_refine_trainSet.py:295 calls it (one pose per call)
+                import contextlib
+                import io
+                total = 0
+                for i in range(n_img):
+                    uv = uv_h[uv_idx[i]].unsqueeze(0).to(dev, non_blocking=True)      # host UV map -> device, per image
+                    with contextlib.redirect_stdout(io.StringIO()):
+                        r.render_path(poses_h[i:i + 1], [H, W, focal], K, 1 << 30, kw, uvMap=uv,
+                                      expType=[exp_slots[i]], savedir=tmp if rank == 0 else None,
+                                      shapeCodes=shapes_img[i:i + 1].to(dev), name=f"img_{i:05d}" if rank == 0 else None)
+                    total += r.last_sink.png_bytes
+                png_bytes[0] = total
+
+    def timed(fn, steps):
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        barrier()
+        for s0, s1 in ev:
+            if world > 1:
+                dist.barrier()
+            s0.record()
+            fn()
+            s1.record()
+        barrier()
+        t = torch.tensor([sum(a.elapsed_time(b) for a, b in ev) / steps], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # warm-up: 3 images' worth (weights packed, tables built, allocator warm); a full step is 20-1200 frames
+    n_save, n_img_w = n_img, min(n_img, 3)
+    if sweep:
+        slots_full, slots = slots, slots[:n_img_w]
+    n_img = n_img_w
+    for _ in range(max(1, args.warmup)):
+        step_device()
+    n_img = n_save
+    if sweep:
+        slots = slots_full
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    eng = r.engine(dev)
+    l0 = eng.launch_count
+    ms_dev = timed(step_device, args.steps)
+    launches = (eng.launch_count - l0) // max(1, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e = timed(step_e2e, args.steps)
+
+    mg_check = None
+    if world > 1:     # outside the timed region: the gathered frame equals rank 0's single-GPU render, bit for bit
+        last = step_device()
+        if rank == 0:
+            r.shard_rays = False
+            with torch.no_grad():
+                if sweep:
+                    alone = r.render_fitting(H, W, K, chunk=1 << 30, c2w=pose, shapeCodes=shape, uvCodes=tex, expType=20,
+                                             expCodes=r.expCodes_Sigma[slots[-1]], **kw)[0]
+                else:
+                    i = n_img - 1
+                    alone = r.render(H, W, K, chunk=1 << 30, c2w=poses_h[i][:3, :4], shapeCodes=shapes_img[i].reshape(1, -1).to(dev),
+                                     uvMap=uv_h[uv_idx[i]].to(dev), expType=exp_slots[i], **kw)[0]
+            same = bool(torch.equal(alone, last))
+            mg_check = {"image": "last of the batch", "rays": H * W, "bit_exact_vs_single_gpu": same}
+            if not same:
+                raise SystemExit("multi-GPU check FAILED: gathered frame differs from the single-GPU render")
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+    rays = n_img * H * W
+    flop = rays * (args.n_samples * FLOP_COARSE_PT + fine_evals(args) * FLOP_FINE_PT)
+    name = ("BASELINE config #4: 20-expression sweep (rendering_modulation), 800x800, render_fitting per image" if sweep else
+            "BASELINE config #5: multi-identity batch (identities x 4 views) through render_path -> render -> texEncoder, 256x256")
+    line = {"metric": f"rays/sec over the image batch ({'sweep20' if sweep else 'ids300'}; FULL: {args.n_samples} coarse + "
+                      f"{fine_evals(args)} fine evaluations/ray)",
+            "value": rays / (ms_dev / 1e3), "unit": "rays/s", "images_per_s": n_img / (ms_dev / 1e3), "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f16 operands / f32 accumulate (fine net); split f16 hi+lo (coarse net); f32 elsewhere",
+            "data": "synthetic",
+            "config": {"workload": f"{name}; {n_img} images of {H}x{W} per step ({rays} rays)"
+                                   + ("" if sweep or n_img == 1200 else f" — a {n_img}-image slice of the 1200-image batch"),
+                       "images_per_step": n_img, "rays_per_step": rays, "parallelism": f"rays of every image sharded x{world}, "
+                       "one all-gather per image", "per_image": "latent re-fold" + ("" if sweep else " + texture encoder + new pose"),
+                       "warmup_note": "warm-up steps render 3 images each"},
+            "clocks": clocks,
+            "e2e": {"value": rays / (ms_e2e / 1e3), "unit": "rays/s", "images_per_s": n_img / (ms_e2e / 1e3), "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": 0 if sweep else int(n_img * 512 * 512 * 3 * 4),
+                    "d2h_bytes_per_step": int(n_img * H * W * (3 if sweep else 4) * 4), "png_bytes_per_step": int(png_bytes[0]),
+                    "api": ("render_fitting(c2w=...) per expression + AsyncImageSink (device->host copy and PNG on a worker thread)"
+                            if sweep else "render_path(...) per image: UV map host->device, texture encoder on a side stream, "
+                            "device->host copy and PNG on a worker thread")},
+            "gpu_launches": int(launches),
+            "whole_step_tflops": flop / world / (ms_dev / 1e3) / 1e12}
+    if mg_check is not None:
+        line["multi_gpu_check"] = mg_check
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     if args.workload in ("fit", "train") and args.impl == "b200":
@@ -362,6 +549,9 @@ def main():
         return
     if not torch.cuda.is_available():
         raise SystemExit("bench.py (engine arm) needs a B200; there is no CPU path. Use --impl reference for the CPU arm.")
+    if args.workload in ("sweep20", "ids300"):
+        run_image_workload(args, rank, world, local_rank)
+        return
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     dist = None

@@ -48,9 +48,9 @@ struct SplitSmem {
 };
 static_assert(SplitSmem::DYN_BYTES <= 232448, "split coarse kernel exceeds the 227 KB shared-memory limit");
 
-// The two epilogue groups finish column blocks {0,2} first and {1,3} second; a layer that waits for a freshly written
-// activation consumes its K blocks in that order (the producer streams the weight K-blocks in the same order).
-__device__ __forceinline__ int split_kb_order(int i, int kb) { return (kb == 4) ? (((i & 1) << 1) | (i >> 1)) : i; }
+// The epilogue finishes the column blocks in ascending order (both groups work on the same block), and a layer consumes
+// its K blocks in that order.
+__device__ __forceinline__ int split_kb_order(int i, int kb) { (void)kb; return i; }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 coarse_split_kernel(const __grid_constant__ CUtensorMap tmX0hi, const __grid_constant__ CUtensorMap tmX0lo,
@@ -88,7 +88,7 @@ coarse_split_kernel(const __grid_constant__ CUtensorMap tmX0hi, const __grid_con
     mbar_init(x0_full, 1);
     mbar_init(mma_done0, 1);
     mbar_init(mma_done0 + 8, 1);
-    for (int i = 0; i < 4; ++i) mbar_init(act_ready0 + 8 * i, 8);   // one arrival per epilogue warp of the block, both CTAs
+    for (int i = 0; i < 4; ++i) mbar_init(act_ready0 + 8 * i, 16);  // one arrival per epilogue warp, both CTAs
     fence_mbar_init();
   }
   __syncthreads();
@@ -241,13 +241,16 @@ coarse_split_kernel(const __grid_constant__ CUtensorMap tmX0hi, const __grid_con
         float hacc[3] = {0.f, 0.f, 0.f};
         const float* hw = d.head == 1 ? w_alpha : w_rgb;
         const int hn = d.head == 1 ? 1 : (d.head == 2 ? 3 : 0);
-        const int ncb = d.n_out >> 6, half_cb = ncb >> 1;
-        // This warp's 32-column chunks of the tile: chunk q covers columns [(grp * half_cb) * 64 + q * 32, +32).  The
+        const int ncb = d.n_out >> 6;
+        // This warp's 32-column chunks of the tile: half `grp` of every 64-column block, blocks in ascending order — both
+        // groups work on block 0 first, so the next layer's K block 0 is complete after a quarter of the epilogue, block 1
+        // after half, ... (with each group owning two whole blocks the first blocks were ready only at half time and the
+        // MMAs of the next layer waited for them).  Chunk q covers columns [q * 64 + grp * 32, +32).  The
         // additive terms of chunk q + 1 (bias, parked skip partial or per-ray view vector) are fetched while chunk q is
         // being processed, and chunk q's own TMEM load is issued before anything else, so the only exposed latency per
         // chunk is the TMEM load itself (with every fetch after the TMEM wait the epilogue was 75 % stalled on them).
-        const int nchunk = 2 * half_cb;
-        const int col0 = grp * half_cb * 64;
+        const int nchunk = ncb;
+        const int col0 = grp * 32;
         auto fetch_add = [&](int ncol, float4 (&ad)[8]) {
           if (d.park) return;
           const float4* bias4 = reinterpret_cast<const float4*>(d.bias + ncol);
@@ -273,11 +276,11 @@ coarse_split_kernel(const __grid_constant__ CUtensorMap tmX0hi, const __grid_con
         fetch_add(col0, ad);
 #pragma unroll 1
         for (int q = 0; q < nchunk; ++q) {
-          const int ncol = col0 + q * 32;
-          const int cb = ncol >> 6, h = (ncol >> 5) & 1;
+          const int ncol = col0 + q * 64;
+          const int cb = q, h = grp;
           uint32_t v[32];
           tmem_ld_32x32b_x32(tmem_base + lane_base + acc * 256 + ncol, v);
-          if (q + 1 < nchunk) fetch_add(ncol + 32, adn);
+          if (q + 1 < nchunk) fetch_add(ncol + 64, adn);
           tmem_ld_wait();
           if (d.park) {            // virtual layer: raw accumulators to the scratch, nothing else
 #pragma unroll
@@ -331,7 +334,7 @@ coarse_split_kernel(const __grid_constant__ CUtensorMap tmX0hi, const __grid_con
           }
 #pragma unroll
           for (int i = 0; i < 8; ++i) ad[i] = adn[i];
-          if (d.store && h == 1) {        // K block cb of the next layer's A operand is complete for this warp's rows
+          if (d.store) {                  // this warp's half of K block cb of the next layer's A operand is complete
             fence_proxy_async_smem();
             tc_fence_before();
             __syncwarp();

@@ -11,8 +11,10 @@ the StyleModule expression modulation.
 from __future__ import annotations
 
 import os
+import threading
 import time
 import warnings
+from concurrent.futures import ThreadPoolExecutor
 from typing import Optional
 
 import numpy as np
@@ -48,6 +50,51 @@ class lossesLog:
             self.lossesDict[name] = 0
             self.chunkDict[name] = 0
         return loss
+
+
+class AsyncImageSink:
+    """Device -> host copy and PNG encoding of finished frames OFF the rendering path (the reference does
+    `rgb.cpu().numpy()` + imageio.imwrite synchronously after every frame, models/render_class.py:224-233).
+
+    submit() enqueues, on the rendering stream, an asynchronous copy of the frame into pinned host memory and records an
+    event; a worker thread waits for that event only, converts to 8 bit and writes the PNG, while the caller goes on
+    enqueueing the next frame.  results() joins everything and returns the float frames in submission order."""
+
+    def __init__(self, workers: int = 2):
+        self._pool = ThreadPoolExecutor(max_workers=workers)
+        self._jobs = []
+        self.png_bytes = 0
+        self._lock = threading.Lock()
+
+    def submit(self, tensors, filename=None):
+        host, ev = [], None
+        for t in tensors:
+            h = torch.empty(t.shape, dtype=t.dtype, pin_memory=t.is_cuda)
+            h.copy_(t.detach(), non_blocking=True)
+            host.append(h)
+        if tensors and tensors[0].is_cuda:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(tensors[0].device))
+
+        def finish():
+            if ev is not None:
+                ev.synchronize()
+            arrays = [h.numpy() for h in host]
+            if filename is not None:
+                _imwrite(filename, to8b(arrays[0]))
+                with self._lock:
+                    self.png_bytes += os.path.getsize(filename)
+            return arrays
+
+        self._jobs.append(self._pool.submit(finish))
+
+    def results(self):
+        out = [j.result() for j in self._jobs]
+        self._jobs = []
+        return out
+
+    def close(self):
+        self._pool.shutdown(wait=True)
 
 
 def _needs_grad(*tensors) -> bool:
@@ -287,17 +334,22 @@ class B200Renderer(torch.nn.Module):
             all_ret = self.batchify_rays(chunk, **kwargs)
         return self._finish(all_ret, sh)
 
+    def _encode_texture(self, uvMap):
+        """texture map -> texture code (models/render_class.py:184)."""
+        enc_dev = next(self.texEncoder.parameters()).device
+        return self.texEncoder(uvMap.permute([2, 0, 1]).unsqueeze(0).to(enc_dev), self.lossList)
+
     def render(self, H, W, K, chunk=1024 * 32, rays=None, c2w=None, ndc=True, shapeCodes=None, uvMap=None,
-               expType=None, near=0., far=1., use_viewdirs=False, c2w_staticcam=None, **kwargs):
-        """models/render_class.py:125-197 -> [rgb_map, disp_map, acc_map, extras]."""
+               expType=None, near=0., far=1., use_viewdirs=False, c2w_staticcam=None, _tex=None, **kwargs):
+        """models/render_class.py:125-197 -> [rgb_map, disp_map, acc_map, extras].
+        _tex (private, used by render_path): the (code, losses) pair of self._encode_texture(uvMap) when it was already
+        computed on a side stream."""
         rays, sh = self._rays_from_args(H, W, K, rays, c2w, ndc, near, far, use_viewdirs, c2w_staticcam)
         self.shapeCodes = shapeCodes
         self.rays = self._to_device(rays)
         self.uvMap = uvMap
         self.expType = expType
-        enc_dev = next(self.texEncoder.parameters()).device
-        self.decoding_texCodes, enlosses = self.texEncoder(uvMap.permute([2, 0, 1]).unsqueeze(0).to(enc_dev),
-                                                           self.lossList)                       # :184
+        self.decoding_texCodes, enlosses = self._encode_texture(uvMap) if _tex is None else _tex         # :184
         self.lossLog.update(enlosses, 1)
         return self._render_all(chunk, sh, **kwargs)
 
@@ -320,31 +372,57 @@ class B200Renderer(torch.nn.Module):
 
     def render_path(self, render_poses, hwf, K, chunk, render_kwargs, uvMap=None, expType=None, gt_imgs=None,
                     savedir=None, render_factor=0, shapeCodes=None, name=None):
-        """models/render_class.py:199-237."""
+        """models/render_class.py:199-237, same arguments, prints and results — but pipelined: while
+        frame i renders, the texture encoder of frame i + 1 runs on a side stream, and the device->host copy + PNG
+        encoding of frame i - 1 run on a worker thread (AsyncImageSink); the rendering stream never waits for the host."""
         H, W, focal = hwf
         if render_factor != 0:
             H = H // render_factor
             W = W // render_factor
             focal = focal / render_factor
-        rgbs, disps = [], []
         t = time.time()
         if savedir is not None:
             filename = os.path.join(savedir, '{}.png'.format(name))
             if os.path.exists(filename):
                 print("exists")
                 return 0, 0
+        n = len(render_poses)
+        cuda = torch.cuda.is_available()
+        side = torch.cuda.Stream() if cuda else None
+        sink = AsyncImageSink()
+        self.last_sink = sink
+
+        def encode_ahead(i):        # texture code of frame i on the side stream; returns (result, event)
+            if side is None or torch.is_grad_enabled():
+                return self._encode_texture(uvMap[i, :]), None
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                res = self._encode_texture(uvMap[i, :])
+                ev = torch.cuda.Event()
+                ev.record(side)
+            res[0].record_stream(torch.cuda.current_stream())     # produced on the side stream, consumed on the main one
+            return res, ev
+
+        ahead = encode_ahead(0) if n > 0 else None
         for i, c2w in enumerate(render_poses):
             print(i, time.time() - t)
             t = time.time()
+            tex, ev = ahead
+            if ev is not None:
+                torch.cuda.current_stream().wait_event(ev)
             rgb, disp, acc, _ = self.render(H, W, K, chunk=chunk, c2w=c2w[:3, :4],
                                             shapeCodes=shapeCodes[i, :].reshape(1, -1), uvMap=uvMap[i, :],
-                                            expType=expType[i], **render_kwargs)
-            rgbs.append(rgb.cpu().numpy())
-            disps.append(disp.cpu().numpy())
+                                            expType=expType[i], _tex=tex, **render_kwargs)
+            if i + 1 < n:
+                ahead = encode_ahead(i + 1)
+            fn = None
             if savedir is not None:
-                rgb8 = to8b(rgbs[-1])
                 fn = os.path.join(savedir, '{}.png'.format(name) if name is not None else '{:03d}.png'.format(i))
-                _imwrite(fn, rgb8)
+            sink.submit([rgb, disp], fn)
+        frames = sink.results()
+        sink.close()
+        rgbs = [f[0] for f in frames]
+        disps = [f[1] for f in frames]
         return np.stack(rgbs, 0), np.stack(disps, 0)
 
 
