@@ -2,6 +2,7 @@
 // of the two MoFaNeRF MLPs and the render_rays orchestration.
 #include "../../include/mofa_b200.h"
 
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -1080,20 +1081,27 @@ int mofa_b200_set_latents(mofa_b200_ctx* c, const float* shape50, const float* e
   return 0;
 }
 
-static int effective_chunk(int64_t n_rays, int chunk_rays) {
-  // default 4144 rays = 2 * 2072, 2072 = 56 * 37 = 7 * 296: with 64 + 128 samples a pass is exactly 112 waves of 74
-  // CTA-pair tiles (fine net, 256x256 tiles, 4 column tiles) and exactly 14 waves of 148 tiles (fused coarse kernel):
-  // no partial last wave, and per-launch prologue/drain (~6 us) stays below 1 % of a ~0.9 ms layer launch
-  int64_t ch = chunk_rays > 0 ? chunk_rays : 4144;
-  if (ch > n_rays) ch = n_rays;
-  if (ch < 1) ch = 1;
-  return static_cast<int>(ch);
+static int effective_chunk(int64_t n_rays, int chunk_rays, int S_last = 128) {
+  // Default: at most 4144 rays per pass (with 64 + 128 samples: 37 slabs of the fine-net chain kernel = 2072 m-blocks,
+  // 14 rounds of coarse pair tiles), and the passes of a call BALANCED: n rays are split into ceil(n / 4144) passes of
+  // equal length, rounded up to whole slabs — a rank's 80 000 rays of an 8-way sharded 800x800 frame become 19 passes of
+  // 4032 rays + one of 3392 instead of 19 x 4144 + a 1264-ray stub whose partial rounds and fixed per-pass work were the
+  // 8-GPU tail of round 1.  An explicit chunk_rays is taken as is (results never depend on the chunking).
+  if (chunk_rays > 0) return static_cast<int>(chunk_rays < n_rays ? chunk_rays : (n_rays > 0 ? n_rays : 1));
+  const int64_t cap = 4144;
+  if (n_rays <= cap) return static_cast<int>(n_rays > 0 ? n_rays : 1);
+  const int64_t passes = (n_rays + cap - 1) / cap;
+  int64_t per = (n_rays + passes - 1) / passes;
+  const int64_t unit = std::max<int64_t>(1, static_cast<int64_t>(chain_slab_mb()) * 256 / (S_last > 0 ? S_last : 1));
+  per = (per + unit - 1) / unit * unit;
+  if (per > cap) per = cap;
+  return static_cast<int>(per);
 }
 
 size_t mofa_b200_workspace_bytes(mofa_b200_ctx* c, int64_t n_rays, int n_samples, int n_importance, int chunk_rays) {
   if (!c) return 0;
-  const int ch = effective_chunk(n_rays, chunk_rays);
   const int S_f = n_importance > 0 ? n_samples + n_importance : 0;
+  const int ch = effective_chunk(n_rays, chunk_rays, S_f > 0 ? S_f : n_samples);
   int Wmax = max_width(c);
   if (Wmax == 0) Wmax = 1024;
   return carve(c, nullptr, ch, n_samples, S_f, Wmax).total + 1024;
@@ -1120,7 +1128,7 @@ int mofa_b200_render_rays_fwd(mofa_b200_ctx* c, const mofa_b200_render_args* a, 
   CK(cudaSetDevice(c->device));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
 
-  int ch = effective_chunk(a->n_rays, a->chunk_rays);
+  int ch = effective_chunk(a->n_rays, a->chunk_rays, S_f > 0 ? S_f : S_c);
   if ((a->flags & MOFA_FLAG_GEMM_SIMT) && ch > 256) ch = 256;    // verification path: per-layer buffers, one row per point
   const int Wmax = max_width(c);
   if (!a->workspace) return fail("render_rays_fwd: workspace is NULL");
