@@ -53,6 +53,18 @@ int mofa_b200_load_weights(mofa_b200_ctx* ctx, int net, int W, int D, const floa
                            int n_tensors, void* stream);
 
 /*
+ * Packed-weight blob (the reference re-reads its .tar state_dicts through torch.load and
+ * load_state_dict on every start, tools/create_model_condition.py:62-89).  export writes the engine's own layout of a
+ * loaded network — fp16 K-major images per concat segment (+ the low images of the split-precision coarse net, + the
+ * transposed copies the backward pass uses), fp32 biases, latent columns and heads — into HOST memory; import rebuilds
+ * the network from such a blob without any fp32 source tensors (and without the PyTorch modules).  The blob is specific
+ * to this library's layout version (checked through its magic) and independent of the device it was made on.
+ */
+size_t mofa_b200_packed_bytes(mofa_b200_ctx* ctx, int net);
+int mofa_b200_export_packed(mofa_b200_ctx* ctx, int net, void* host_dst, size_t bytes, void* stream);
+int mofa_b200_import_packed(mofa_b200_ctx* ctx, int net, const void* host_src, size_t bytes, void* stream);
+
+/*
  * Per-call latent conditioning (models/render_class.py:74-85,104): shape code [50], modulated
  * expression code exp_scale*expCodes_Sigma[expType]+exp_bias [30], texture code [256]; device fp32.
  * Folds the latent columns of the five concat layers of each loaded net into per-layer bias vectors.

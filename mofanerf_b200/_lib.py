@@ -57,6 +57,9 @@ SIGNATURES = {
     "mofa_b200_destroy": (C.c_int, [C.c_void_p]),
     "mofa_b200_load_weights": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_int,
                                          C.c_void_p]),
+    "mofa_b200_packed_bytes": (C.c_size_t, [C.c_void_p, C.c_int]),
+    "mofa_b200_export_packed": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "mofa_b200_import_packed": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "mofa_b200_set_latents": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mofa_b200_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int]),
     "mofa_b200_render_rays_fwd": (C.c_int, [C.c_void_p, C.POINTER(RenderArgs), C.c_void_p]),

@@ -104,6 +104,9 @@ struct Net {
   int split_n = 0;
   float* w_view = nullptr;
   std::vector<void*> allocs;
+  // the allocations that hold WEIGHT DATA (packed fp16 images, biases, latent columns, heads), in creation order —
+  // what mofa_b200_export_packed writes and mofa_b200_import_packed restores; derived tables are rebuilt on import
+  std::vector<std::pair<void*, size_t>> data_allocs;
 };
 
 }  // namespace
@@ -117,6 +120,7 @@ struct mofa_b200_ctx {
   bool latents_set = false;
   bool pair_kernel = true;       // cta_group::2 kernel for N % 256 == 0 (MOFA_B200_DENSE_1CTA=1 disables)
   bool fused_coarse = true;      // one persistent kernel for a W == 256 net (MOFA_B200_NO_FUSED_COARSE=1 disables)
+  bool importing = false;        // load_weights is being driven by mofa_b200_import_packed: build the structure, read no sources
   bool chain_fine = true;        // all dense layers of a W >= 512 net in one persistent launch, activations L2-resident
                                  // (fine_chain.cu); MOFA_B200_FINE_PER_LAYER=1 selects one launch per layer (round 1)
   // device tables of the chain kernel (tensor maps + layer descriptors), rebuilt when the buffers they point to change
@@ -161,6 +165,11 @@ int dev_alloc(Net& n, void** p, size_t bytes) {
   n.allocs.push_back(*p);
   return 0;
 }
+int dev_alloc_data(Net& n, void** p, size_t bytes) {
+  if (dev_alloc(n, p, bytes)) return 1;
+  n.data_allocs.emplace_back(*p, bytes);
+  return 0;
+}
 
 void free_net(Net& n) {
   for (void* p : n.allocs) cudaFree(p);
@@ -183,6 +192,7 @@ struct LayerSpec {
 };
 
 int build_layer(mofa_b200_ctx* c, Net& net, const LayerSpec& sp, const float* w, const float* b, cudaStream_t s) {
+  const bool imp = c->importing;
   Layer L;
   L.N = sp.N;
   L.nseg = sp.nseg;
@@ -194,36 +204,43 @@ int build_layer(mofa_b200_ctx* c, Net& net, const LayerSpec& sp, const float* w,
     L.K[i] = sp.seg_kpad[i];
     L.seg_c0[i] = sp.seg_c0[i];
     L.seg_kreal[i] = sp.seg_k[i];
-    if (dev_alloc(net, reinterpret_cast<void**>(&L.w[i]), sizeof(__half) * (size_t)sp.N * L.K[i])) return 1;
-    CK(launch_pack_weight(w, sp.in_total, sp.seg_c0[i], sp.seg_k[i], L.K[i], sp.N, L.w[i], s));
-    c->launches++;
+    if (dev_alloc_data(net, reinterpret_cast<void**>(&L.w[i]), sizeof(__half) * (size_t)sp.N * L.K[i])) return 1;
+    if (!imp) {
+      CK(launch_pack_weight(w, sp.in_total, sp.seg_c0[i], sp.seg_k[i], L.K[i], sp.N, L.w[i], s));
+      c->launches++;
+    }
     if (make_tmap_2d(c, &L.tmB[i], L.w[i], sp.N, L.K[i], L.K[i], L.BN)) return 1;
     if (make_tmap_2d(c, &L.tmB2[i], L.w[i], sp.N, L.K[i], L.K[i], 128)) return 1;
     if (net.W == 256) {
-      if (dev_alloc(net, reinterpret_cast<void**>(&L.wlo[i]), sizeof(__half) * (size_t)sp.N * L.K[i])) return 1;
-      CK(launch_pack_weight_lo(w, sp.in_total, sp.seg_c0[i], sp.seg_k[i], L.K[i], sp.N, L.wlo[i], s));
-      c->launches++;
+      if (dev_alloc_data(net, reinterpret_cast<void**>(&L.wlo[i]), sizeof(__half) * (size_t)sp.N * L.K[i])) return 1;
+      if (!imp) {
+        CK(launch_pack_weight_lo(w, sp.in_total, sp.seg_c0[i], sp.seg_k[i], L.K[i], sp.N, L.wlo[i], s));
+        c->launches++;
+      }
       if (make_tmap_2d(c, &L.tmS_hi[i], L.w[i], sp.N, L.K[i], L.K[i], sp.N / 2)) return 1;
       if (make_tmap_2d(c, &L.tmS_lo[i], L.wlo[i], sp.N, L.K[i], L.K[i], sp.N / 2)) return 1;
     }
     L.rows_t[i] = L.K[i] < 128 ? 128 : L.K[i];
     L.BN_t[i] = (L.rows_t[i] % 256 == 0) ? 256 : 128;
-    if (dev_alloc(net, reinterpret_cast<void**>(&L.wt[i]), sizeof(__half) * (size_t)L.rows_t[i] * sp.N)) return 1;
-    CK(launch_pack_weight_t(w, sp.in_total, sp.seg_c0[i], sp.seg_k[i], L.rows_t[i], sp.N, L.wt[i], s));
-    c->launches++;
+    if (dev_alloc_data(net, reinterpret_cast<void**>(&L.wt[i]), sizeof(__half) * (size_t)L.rows_t[i] * sp.N)) return 1;
+    if (!imp) {
+      CK(launch_pack_weight_t(w, sp.in_total, sp.seg_c0[i], sp.seg_k[i], L.rows_t[i], sp.N, L.wt[i], s));
+      c->launches++;
+    }
     if (make_tmap_2d(c, &L.tmBt[i], L.wt[i], L.rows_t[i], sp.N, sp.N, L.BN_t[i])) return 1;
     if (make_tmap_2d(c, &L.tmBt2[i], L.wt[i], L.rows_t[i], sp.N, sp.N, 128)) return 1;
   }
-  if (dev_alloc(net, reinterpret_cast<void**>(&L.bias_raw), sizeof(float) * sp.N)) return 1;
-  CK(cudaMemcpyAsync(L.bias_raw, b, sizeof(float) * sp.N, cudaMemcpyDeviceToDevice, s));
+  if (dev_alloc_data(net, reinterpret_cast<void**>(&L.bias_raw), sizeof(float) * sp.N)) return 1;
+  if (!imp) CK(cudaMemcpyAsync(L.bias_raw, b, sizeof(float) * sp.N, cudaMemcpyDeviceToDevice, s));
   L.bias_eff = L.bias_raw;
   if (sp.fold_n > 0) {
     L.fold_n = sp.fold_n;
     L.fold_lat = sp.fold_lat;
     L.fold_c0 = sp.fold_c0;
-    if (dev_alloc(net, reinterpret_cast<void**>(&L.fold_w), sizeof(float) * (size_t)sp.N * sp.fold_n)) return 1;
-    CK(cudaMemcpy2DAsync(L.fold_w, sizeof(float) * sp.fold_n, w + sp.fold_c0, sizeof(float) * sp.in_total,
-                         sizeof(float) * sp.fold_n, sp.N, cudaMemcpyDeviceToDevice, s));
+    if (dev_alloc_data(net, reinterpret_cast<void**>(&L.fold_w), sizeof(float) * (size_t)sp.N * sp.fold_n)) return 1;
+    if (!imp)
+      CK(cudaMemcpy2DAsync(L.fold_w, sizeof(float) * sp.fold_n, w + sp.fold_c0, sizeof(float) * sp.in_total,
+                           sizeof(float) * sp.fold_n, sp.N, cudaMemcpyDeviceToDevice, s));
     if (dev_alloc(net, reinterpret_cast<void**>(&L.bias_eff), sizeof(float) * sp.N)) return 1;
   }
   net.layers.push_back(L);
@@ -870,7 +887,9 @@ int mofa_b200_load_weights(mofa_b200_ctx* c, int net_id, int W, int D, const flo
   CK(cudaSetDevice(c->device));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   Net& net = c->nets[net_id];
-  if (net.loaded && net.W == W && net.D == D) {
+  const bool imp = c->importing;
+  if (!imp && !t) return fail("load_weights: tensors is NULL");
+  if (!imp && net.loaded && net.W == W && net.D == D) {
     // Same architecture (a training step changed the values): repack into the existing buffers — no allocation, tensor
     // maps and the fused-kernel tables stay valid.
     const int nd = static_cast<int>(net.layers.size());
@@ -903,12 +922,14 @@ int mofa_b200_load_weights(mofa_b200_ctx* c, int net_id, int W, int D, const flo
     return 0;
   }
   free_net(net);
+  for (int i = 0; i < 4; ++i) c->chain_key[i] = nullptr;     // the chain kernel's tables point into the freed network
   net.W = W;
   net.D = D;
   int ti = 0;
   auto next = [&](const float*& w, const float*& b) {
-    w = t[ti++];
-    b = t[ti++];
+    w = imp ? nullptr : t[ti];
+    b = imp ? nullptr : t[ti + 1];
+    ti += 2;
   };
   const float *w, *b;
   ProgBuilder pb(net);
@@ -992,22 +1013,27 @@ int mofa_b200_load_weights(mofa_b200_ctx* c, int net_id, int W, int D, const flo
     if (build_layer(c, net, sp, w, b, s)) return 1;
     pb.dense(li++, SRC_V, pb.cur);
     if (W == 256) {   // fp32 view-direction columns for the per-ray view vector of the split-precision kernel
-      if (dev_alloc(net, reinterpret_cast<void**>(&net.w_view), sizeof(float) * kPeView * (W / 2))) return 1;
-      CK(cudaMemcpy2DAsync(net.w_view, sizeof(float) * kPeView, w, sizeof(float) * (kPeView + W), sizeof(float) * kPeView,
-                           W / 2, cudaMemcpyDeviceToDevice, s));
+      if (dev_alloc_data(net, reinterpret_cast<void**>(&net.w_view), sizeof(float) * kPeView * (W / 2))) return 1;
+      if (!imp)
+        CK(cudaMemcpy2DAsync(net.w_view, sizeof(float) * kPeView, w, sizeof(float) * (kPeView + W), sizeof(float) * kPeView,
+                             W / 2, cudaMemcpyDeviceToDevice, s));
     }
   }
   // alpha_linear (W -> 1), rgb_linear (W/2 -> 3): fp32 copies for the SIMT heads
   next(w, b);
-  if (dev_alloc(net, reinterpret_cast<void**>(&net.w_alpha), sizeof(float) * W)) return 1;
-  if (dev_alloc(net, reinterpret_cast<void**>(&net.b_alpha), sizeof(float))) return 1;
-  CK(cudaMemcpyAsync(net.w_alpha, w, sizeof(float) * W, cudaMemcpyDeviceToDevice, s));
-  CK(cudaMemcpyAsync(net.b_alpha, b, sizeof(float), cudaMemcpyDeviceToDevice, s));
+  if (dev_alloc_data(net, reinterpret_cast<void**>(&net.w_alpha), sizeof(float) * W)) return 1;
+  if (dev_alloc_data(net, reinterpret_cast<void**>(&net.b_alpha), sizeof(float))) return 1;
+  if (!imp) {
+    CK(cudaMemcpyAsync(net.w_alpha, w, sizeof(float) * W, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(net.b_alpha, b, sizeof(float), cudaMemcpyDeviceToDevice, s));
+  }
   next(w, b);
-  if (dev_alloc(net, reinterpret_cast<void**>(&net.w_rgb), sizeof(float) * 3 * (W / 2))) return 1;
-  if (dev_alloc(net, reinterpret_cast<void**>(&net.b_rgb), sizeof(float) * 3)) return 1;
-  CK(cudaMemcpyAsync(net.w_rgb, w, sizeof(float) * 3 * (W / 2), cudaMemcpyDeviceToDevice, s));
-  CK(cudaMemcpyAsync(net.b_rgb, b, sizeof(float) * 3, cudaMemcpyDeviceToDevice, s));
+  if (dev_alloc_data(net, reinterpret_cast<void**>(&net.w_rgb), sizeof(float) * 3 * (W / 2))) return 1;
+  if (dev_alloc_data(net, reinterpret_cast<void**>(&net.b_rgb), sizeof(float) * 3)) return 1;
+  if (!imp) {
+    CK(cudaMemcpyAsync(net.w_rgb, w, sizeof(float) * 3 * (W / 2), cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(net.b_rgb, b, sizeof(float) * 3, cudaMemcpyDeviceToDevice, s));
+  }
   {
     for (auto it = net.program.rbegin(); it != net.program.rend(); ++it)
       if (it->kind == 0) {
@@ -1062,7 +1088,96 @@ int mofa_b200_load_weights(mofa_b200_ctx* c, int net_id, int W, int D, const flo
   }
   if (W == 256 && build_split_table(c, net, s)) return 1;
   net.loaded = true;
-  if (c->latents_set && fold_net(c, net, s)) return 1;
+  if (!imp && c->latents_set && fold_net(c, net, s)) return 1;
+  return 0;
+}
+
+// ---- packed-weight blob: the engine's own layout of one network, for an on-disk cache ----------
+namespace {
+struct PackedHeader {
+  char magic[8];          // "MOFAPK02"
+  int32_t W, D, n_allocs, reserved;
+  uint64_t total_bytes;   // header + table of sizes + data
+};
+const char kPackedMagic[8] = {'M', 'O', 'F', 'A', 'P', 'K', '0', '2'};
+size_t packed_total(const Net& n) {
+  size_t t = sizeof(PackedHeader) + sizeof(uint64_t) * n.data_allocs.size();
+  for (const auto& a : n.data_allocs) t += (a.second + 15) / 16 * 16;
+  return t;
+}
+}  // namespace
+
+size_t mofa_b200_packed_bytes(mofa_b200_ctx* c, int net_id) {
+  if (!c || net_id < 0 || net_id > 1 || !c->nets[net_id].loaded) return 0;
+  return packed_total(c->nets[net_id]);
+}
+
+int mofa_b200_export_packed(mofa_b200_ctx* c, int net_id, void* host_dst, size_t bytes, void* stream) {
+  if (!c || net_id < 0 || net_id > 1 || !c->nets[net_id].loaded) return fail("export_packed: net %d not loaded", net_id);
+  const Net& n = c->nets[net_id];
+  if (!host_dst || bytes < packed_total(n)) return fail("export_packed: buffer too small (%zu < %zu)", bytes, packed_total(n));
+  CK(cudaSetDevice(c->device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  uint8_t* p = static_cast<uint8_t*>(host_dst);
+  PackedHeader h;
+  memset(&h, 0, sizeof(h));
+  memcpy(h.magic, kPackedMagic, 8);
+  h.W = n.W; h.D = n.D; h.n_allocs = static_cast<int32_t>(n.data_allocs.size());
+  h.total_bytes = packed_total(n);
+  memcpy(p, &h, sizeof(h));
+  p += sizeof(h);
+  for (const auto& a : n.data_allocs) {
+    const uint64_t sz = a.second;
+    memcpy(p, &sz, sizeof(sz));
+    p += sizeof(sz);
+  }
+  for (const auto& a : n.data_allocs) {
+    CK(cudaMemcpyAsync(p, a.first, a.second, cudaMemcpyDeviceToHost, s));
+    p += (a.second + 15) / 16 * 16;
+  }
+  CK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int mofa_b200_import_packed(mofa_b200_ctx* c, int net_id, const void* host_src, size_t bytes, void* stream) {
+  if (!c) return fail("import_packed: ctx is NULL");
+  if (net_id < 0 || net_id > 1) return fail("import_packed: net must be 0 or 1");
+  if (!host_src || bytes < sizeof(PackedHeader)) return fail("import_packed: blob too small");
+  PackedHeader h;
+  memcpy(&h, host_src, sizeof(h));
+  if (memcmp(h.magic, kPackedMagic, 8) != 0) return fail("import_packed: not a mofa_b200 packed-weight blob (or an older layout)");
+  if (h.total_bytes != bytes) return fail("import_packed: blob is %zu bytes, header says %llu", bytes, (unsigned long long)h.total_bytes);
+  const int n2 = h.D - 5;
+  const int expect = 2 * (4 + 2 * (5 + n2) + 3);
+  CK(cudaSetDevice(c->device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  free_net(c->nets[net_id]);
+  c->importing = true;
+  const int rc = mofa_b200_load_weights(c, net_id, h.W, h.D, nullptr, expect, stream);
+  c->importing = false;
+  if (rc) return rc;
+  Net& n = c->nets[net_id];
+  if (static_cast<int>(n.data_allocs.size()) != h.n_allocs || packed_total(n) != bytes) {
+    free_net(n);
+    return fail("import_packed: blob layout does not match this build (allocs %d vs %zu)", h.n_allocs, n.data_allocs.size());
+  }
+  const uint8_t* p = static_cast<const uint8_t*>(host_src) + sizeof(PackedHeader);
+  for (const auto& a : n.data_allocs) {
+    uint64_t sz;
+    memcpy(&sz, p, sizeof(sz));
+    p += sizeof(sz);
+    if (sz != a.second) {
+      free_net(n);
+      return fail("import_packed: tensor size mismatch");
+    }
+  }
+  for (const auto& a : n.data_allocs) {
+    CK(cudaMemcpyAsync(a.first, p, a.second, cudaMemcpyHostToDevice, s));
+    p += (a.second + 15) / 16 * 16;
+  }
+  CK(cudaStreamSynchronize(s));      // the caller's buffer may go away
+  if (c->latents_set && fold_net(c, n, s)) return 1;
+  for (int i = 0; i < 4; ++i) c->chain_key[i] = nullptr;     // device tables point into the freed network
   return 0;
 }
 

@@ -94,6 +94,27 @@ class Engine:
         self._keep[("net", which)] = dev
         self._net_keys[which] = key
 
+    def export_packed(self, which: int):
+        """The engine's own layout of network `which` as a host byte array (numpy uint8) — see mofa_b200_export_packed."""
+        import numpy as np
+        n = int(self.lib.mofa_b200_packed_bytes(self._h, which))
+        if n == 0:
+            raise RuntimeError(f"mofa_b200: network {which} is not loaded")
+        buf = np.empty(n, dtype=np.uint8)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.mofa_b200_export_packed(self._h, which, buf.ctypes.data, n, self._stream()))
+        return buf
+
+    def import_packed(self, which: int, blob, key=None) -> None:
+        """Rebuild network `which` from an export_packed() blob: no fp32 tensors, no PyTorch modules involved.
+        key: the cache key (Engine._key(net)) under which later load_network(net) calls should find it already loaded."""
+        import numpy as np
+        blob = np.ascontiguousarray(np.frombuffer(blob, dtype=np.uint8) if not isinstance(blob, np.ndarray) else blob)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.mofa_b200_import_packed(self._h, which, blob.ctypes.data, blob.size, self._stream()))
+        self._keep.pop(("net", which), None)
+        self._net_keys[which] = key
+
     def set_latents(self, shape: torch.Tensor, exp_mod: torch.Tensor, tex: torch.Tensor) -> None:
         s = _f32c(shape.reshape(-1)[:50], self.device)
         e = _f32c(exp_mod.reshape(-1), self.device)

@@ -190,6 +190,8 @@ class B200Renderer(torch.nn.Module):
                     gemm_simt=False):
         """models/render_class.py:239-352.  Extra keyword-only inputs (t_rand/u/noise_*) feed explicit random
         numbers for parity tests; with pytest=True they default to the reference's seeded numpy draws."""
+        if network_fine is not None and getattr(network_fine, "module", network_fine) is None:
+            network_fine = None       # run_fit.py:167 wraps create_nerf's None (N_importance == 0) in DataParallel
         rays = self.rays[ray_batch[0]:ray_batch[1]]
         if rays.shape[-1] < 11:
             raise NotImplementedError("use_viewdirs=False is not supported (the MoFaNeRF nets require view dirs)")
