@@ -277,7 +277,8 @@ def workload_config(args):
     return {"workload": f"{args.H}x{args.W} frame ({args.H * args.W} rays), {pipe}, "
                         "single identity, perturb=0 (render_kwargs_test)",
             "rays_per_step": args.H * args.W, "parallelism": f"ray-sharded x{args.gpus}",
-            "l2": "working set (activation buffers, >1 GB per pass) >> 126 MB L2; 256 MB scratch write between timed steps"}
+            "l2": "per-point buffers of a pass (encodings, head partials: >250 MB) and the frame's 155 passes >> 126 MB L2; "
+                  "256 MB scratch write between timed steps"}
 
 
 def run_fit_workload(args, train=False):
@@ -670,7 +671,9 @@ def main():
     fine_p = prof[1]
     ach_tf = (fine_p["algo_flops"] / (fine_p["ms"] / 1e3)) / 1e12 if fine_p["ms"] > 0 else 0.0
     traffic = None
-    ncu_json = os.path.join(ROOT, "profiles", "ncu_dense_tc_summary.json")
+    ncu_json = os.path.join(ROOT, "profiles", "ncu_fine_chain_summary.json")
+    if os.environ.get("MOFA_B200_FINE_PER_LAYER") == "1":
+        ncu_json = os.path.join(ROOT, "profiles", "ncu_dense_tc_summary.json")
     if os.path.exists(ncu_json):
         try:
             traffic = json.load(open(ncu_json)).get("dram_bytes_per_launch")
@@ -678,16 +681,20 @@ def main():
             traffic = None
     n_loc = hi - lo
     flop_step = n_loc * (args.n_samples * FLOP_COARSE_PT + fine_evals(args) * FLOP_FINE_PT)
-    dom, dom_name = fine_p, "dense_tc2_kernel<6,0,8,1> (fine-net layers; tcgen05.mma.cta_group::2 kind::f16, 256x256 pair tiles)"
+    dom, dom_name = fine_p, ("fine_chain_kernel (all 25 dense layers of the fine net per launch; tcgen05.mma.cta_group::2 kind::f16, "
+                             "256x256 pair tiles, L2-resident activation slabs)")
+    if os.environ.get("MOFA_B200_FINE_PER_LAYER") == "1":
+        dom_name = "dense_tc2_kernel<6,0,8,1> (fine-net layers, one launch each; tcgen05.mma.cta_group::2 kind::f16, 256x256 pair tiles)"
     if fine_p["ms"] <= 0:        # COARSE64: the only dense work is the fused coarse kernel
-        dom, dom_name = prof[0], "coarse_fused_kernel (whole coarse net per launch; tcgen05.mma kind::f16, activations in smem)"
+        dom, dom_name = prof[0], "coarse_split_kernel (whole coarse net per launch; tcgen05.mma.cta_group::2 kind::f16 x3 split precision, activations in smem)"
         ach_tf = (dom["algo_flops"] / (dom["ms"] / 1e3)) / 1e12 if dom["ms"] > 0 else 0.0
         traffic = None
     line = {
         "metric": metric_name(args),
         "value": rays_per_s, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f16 operands / f32 accumulate (dense layers); f32 elsewhere", "data": "synthetic",
+        "dtype": "f16 operands / f32 accumulate (fine net); split f16 hi+lo operands / f32 accumulate (coarse net); f32 elsewhere",
+        "data": "synthetic",
         "config": workload_config(args),
         "clocks": clocks,
         "e2e": {"value": e2e_rays, "unit": "rays/s", "ms_per_step": ms_e2e,

@@ -274,24 +274,25 @@ coarse_split_kernel(const __grid_constant__ CUtensorMap tmX0hi, const __grid_con
 #pragma unroll
         for (int i = 0; i < 8; ++i) ad[i] = adn[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         fetch_add(col0, ad);
-#pragma unroll 1
-        for (int q = 0; q < nchunk; ++q) {
+        // one chunk; `cur` holds its additive terms, `nxt` receives the next chunk's (the caller alternates the two
+        // arrays, so no register copies are needed between chunks)
+        auto do_chunk = [&](const int q, float4 (&cur)[8], float4 (&nxt)[8]) {
           const int ncol = col0 + q * 64;
           const int cb = q, h = grp;
           uint32_t v[32];
           tmem_ld_32x32b_x32(tmem_base + lane_base + acc * 256 + ncol, v);
-          if (q + 1 < nchunk) fetch_add(ncol + 64, adn);
+          if (q + 1 < nchunk) fetch_add(ncol + 64, nxt);
           tmem_ld_wait();
           if (d.park) {            // virtual layer: raw accumulators to the scratch, nothing else
 #pragma unroll
             for (int i = 0; i < 8; ++i)
               park4[(ncol / 4 + i) * 128 + row] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
                                                               __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
-            continue;
+            return;
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const float4 a0 = ad[2 * j], a1 = ad[2 * j + 1];
+            const float4 a0 = cur[2 * j], a1 = cur[2 * j + 1];
             float f[8];
             f[0] = fmaxf(__uint_as_float(v[j * 8 + 0]) + a0.x, 0.f);
             f[1] = fmaxf(__uint_as_float(v[j * 8 + 1]) + a0.y, 0.f);
@@ -332,8 +333,6 @@ coarse_split_kernel(const __grid_constant__ CUtensorMap tmX0hi, const __grid_con
                            : "memory");
             }
           }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) ad[i] = adn[i];
           if (d.store) {                  // this warp's half of K block cb of the next layer's A operand is complete
             fence_proxy_async_smem();
             tc_fence_before();
@@ -348,6 +347,11 @@ coarse_split_kernel(const __grid_constant__ CUtensorMap tmX0hi, const __grid_con
               else mbar_arrive_cluster(mapa_u32(act_ready0 + 8 * cb, 0));
             }
           }
+        };
+#pragma unroll 1
+        for (int q = 0; q < nchunk; q += 2) {
+          do_chunk(q, ad, adn);
+          do_chunk(q + 1, adn, ad);        // n_out is 128 or 256: always an even number of chunks
         }
         if (hn > 0) {                     // combine the two groups' partial dot products (rows are shared, columns split)
           if (grp == 1) {
