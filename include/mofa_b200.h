@@ -168,6 +168,8 @@ typedef struct mofa_b200_bwd_args {
   int32_t n_params_fine;
   void* workspace;
   size_t workspace_bytes;
+  const float* loss_scale_dev; /* optional: DEVICE pointer to {scale, 1/scale}; when set it replaces loss_scale, so the caller
+                                  can derive the scale from the upstream gradients on the device without a host sync */
 } mofa_b200_bwd_args;
 
 int mofa_b200_render_rays_bwd(mofa_b200_ctx* ctx, const mofa_b200_bwd_args* args, void* stream);

@@ -43,6 +43,7 @@ class BwdArgs(C.Structure):
         ("d_params_coarse", C.c_void_p), ("d_params_fine", C.c_void_p),
         ("n_params_coarse", C.c_int32), ("n_params_fine", C.c_int32),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+        ("loss_scale_dev", C.c_void_p),
     ]
 
 

@@ -53,12 +53,19 @@ class RenderRaysFn(torch.autograd.Function):
         g = dict(zip(ctx.keys, grads))
         d_rgb, d_acc = g.get("rgb_map"), g.get("acc_map")
         d_rgb0, d_acc0 = g.get("rgb0"), g.get("acc0")
-        amax = max([float(x.detach().abs().max()) for x in (d_rgb, d_acc, d_rgb0, d_acc0) if x is not None] + [0.0])
         # power-of-two loss scale: largest upstream gradient -> 2^13 in the fp16 inter-layer gradients.  Per-sample
         # gradients are ~1e-3 .. 1e-4 of the largest one (compositing weights), and fp16 keeps full precision only above
         # 6e-5; the epilogue clamps at +-65504, so an outlier saturates instead of overflowing.
-        scale = 2.0 ** round(math.log2(8192.0 / amax)) if amax > 0 else 1.0
-        scale = min(max(scale, 2.0 ** -20), 2.0 ** 40)
+        # Computed ON THE DEVICE ({scale, 1/scale} -> mofa_b200_bwd_args.loss_scale_dev): the host never waits for the GPU
+        # here (round 1 did `float(tensor.max())` per upstream gradient: four synchronisations per backward).
+        ups = [x.detach().abs().max() for x in (d_rgb, d_acc, d_rgb0, d_acc0) if x is not None]
+        if ups:
+            amax = torch.stack(ups).max().float()
+            sc = torch.exp2(torch.round(torch.log2(8192.0 / amax.clamp_min(1e-30)))).clamp(2.0 ** -20, 2.0 ** 40)
+            sc = torch.where((amax > 0) & torch.isfinite(amax), sc, torch.ones_like(sc))
+            scale = torch.stack([sc, 1.0 / sc]).contiguous()
+        else:
+            scale = 1.0
         cfg = ctx.cfg
         grads_p, pg = [], None
         if ctx.param_shapes:      # training: weight gradients of the coarse (and fine) network, canonical order

@@ -18,7 +18,8 @@ constexpr int kBwdMaxPer = 8;   // S <= 256
 
 __global__ void composite_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
                                      const float* __restrict__ rays, int stride, const float* __restrict__ noise,
-                                     const float* __restrict__ d_rgb, const float* __restrict__ d_acc, float gscale,
+                                     const float* __restrict__ d_rgb, const float* __restrict__ d_acc, float gscale_h,
+                                     const float* __restrict__ sc,
                                      int64_t n, int S, int white_bkgd, float* __restrict__ d_raw,
                                      float* __restrict__ d_rays) {
   const int lane = threadIdx.x & 31;
@@ -29,6 +30,7 @@ __global__ void composite_bwd_kernel(const float* __restrict__ raw, const float*
   const float nd = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
   const float* zr = z + r * S;
   const float4* rr = reinterpret_cast<const float4*>(raw) + r * S;
+  const float gscale = gscale_h * (sc ? __ldg(sc) : 1.0f);     // host factor x optional device-resident factor
   const float gr = d_rgb ? d_rgb[r * 3 + 0] * gscale : 0.f;
   const float gg = d_rgb ? d_rgb[r * 3 + 1] * gscale : 0.f;
   const float gb = d_rgb ? d_rgb[r * 3 + 2] * gscale : 0.f;
@@ -117,10 +119,10 @@ __global__ void composite_bwd_kernel(const float* __restrict__ raw, const float*
 
 cudaError_t launch_composite_bwd(const float* raw, const float* z, const float* rays, int stride, const float* noise,
                                  const float* d_rgb, const float* d_acc, float gscale, int64_t n, int S,
-                                 int white_bkgd, float* d_raw, float* d_rays, cudaStream_t s) {
+                                 int white_bkgd, float* d_raw, float* d_rays, cudaStream_t s, const float* sc) {
   if (n == 0) return cudaSuccess;
   composite_bwd_kernel<<<static_cast<unsigned>((n + 3) / 4), 128, 0, s>>>(raw, z, rays, stride, noise, d_rgb, d_acc,
-                                                                         gscale, n, S, white_bkgd, d_raw, d_rays);
+                                                                         gscale, sc, n, S, white_bkgd, d_raw, d_rays);
   return cudaGetLastError();
 }
 
@@ -176,7 +178,8 @@ cudaError_t launch_colsum(const __half* dZ, int N, int64_t P, float* out, cudaSt
 
 // d_lat[j] += inv_scale * sum_n fold_w[n, j] * d_beff[n]
 __global__ void fold_bwd_kernel(const float* __restrict__ fold_w, int nlat, int N, const float* __restrict__ d_beff,
-                                float inv_scale, float* __restrict__ d_lat) {
+                                float inv_scale_h, float* __restrict__ d_lat, const float* __restrict__ sc) {
+  const float inv_scale = inv_scale_h * (sc ? __ldg(sc) : 1.0f);
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= nlat) return;
   float acc = 0.f;
@@ -185,8 +188,8 @@ __global__ void fold_bwd_kernel(const float* __restrict__ fold_w, int nlat, int 
 }
 
 cudaError_t launch_fold_bwd(const float* fold_w, int nlat, int N, const float* d_beff, float inv_scale, float* d_lat,
-                            cudaStream_t s) {
-  fold_bwd_kernel<<<(nlat + 63) / 64, 64, 0, s>>>(fold_w, nlat, N, d_beff, inv_scale, d_lat);
+                            cudaStream_t s, const float* sc) {
+  fold_bwd_kernel<<<(nlat + 63) / 64, 64, 0, s>>>(fold_w, nlat, N, d_beff, inv_scale, d_lat, sc);
   return cudaGetLastError();
 }
 
@@ -278,36 +281,39 @@ cudaError_t launch_pack_weight_t(const float* src, int ld, int c0, int K, int kr
 }
 
 // y[i] += a * x[i]
-__global__ void axpy_f32_kernel(const float* __restrict__ x, float a, float* __restrict__ y, int n) {
+__global__ void axpy_f32_kernel(const float* __restrict__ x, float a, float* __restrict__ y, int n,
+                                const float* __restrict__ sc) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) y[i] += a * x[i];
+  if (i < n) y[i] += a * (sc ? __ldg(sc) : 1.0f) * x[i];
 }
-cudaError_t launch_axpy_f32(const float* x, float a, float* y, int n, cudaStream_t s) {
+cudaError_t launch_axpy_f32(const float* x, float a, float* y, int n, cudaStream_t s, const float* sc) {
   if (n == 0) return cudaSuccess;
-  axpy_f32_kernel<<<(n + 255) / 256, 256, 0, s>>>(x, a, y, n);
+  axpy_f32_kernel<<<(n + 255) / 256, 256, 0, s>>>(x, a, y, n, sc);
   return cudaGetLastError();
 }
 
 // G[r * ld + c0 + j] += a * u[r] * v[j]      (latent columns of a folded layer: d bias (x) latent)
 __global__ void outer_add_kernel(const float* __restrict__ u, const float* __restrict__ v, int rows, int cols, float a,
-                                 float* __restrict__ G, int ld, int c0) {
+                                 float* __restrict__ G, int ld, int c0, const float* __restrict__ sc) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * cols) return;
   const int r = i / cols, j = i % cols;
-  G[static_cast<size_t>(r) * ld + c0 + j] += a * u[r] * v[j];
+  G[static_cast<size_t>(r) * ld + c0 + j] += a * (sc ? __ldg(sc) : 1.0f) * u[r] * v[j];
 }
 cudaError_t launch_outer_add(const float* u, const float* v, int rows, int cols, float a, float* G, int ld, int c0,
-                             cudaStream_t s) {
+                             cudaStream_t s, const float* sc) {
   const int tot = rows * cols;
   if (tot == 0) return cudaSuccess;
-  outer_add_kernel<<<(tot + 255) / 256, 256, 0, s>>>(u, v, rows, cols, a, G, ld, c0);
+  outer_add_kernel<<<(tot + 255) / 256, 256, 0, s>>>(u, v, rows, cols, a, G, ld, c0, sc);
   return cudaGetLastError();
 }
 
 // Head weight gradients: gW[q, c] += a * sum_p g[p*4 + q0 + q] * act[p, c];  gb[q] += a * sum_p g[p*4 + q0 + q]
 // grid (N/64, row blocks of 2048); 256 threads = 64 columns x 4 row phases
 __global__ void head_wgrad_kernel(const float* __restrict__ g, int q0, int nq, const __half* __restrict__ act, int N,
-                                  int64_t P, float a, float* __restrict__ gW, float* __restrict__ gb) {
+                                  int64_t P, float a_h, float* __restrict__ gW, float* __restrict__ gb,
+                                  const float* __restrict__ sc) {
+  const float a = a_h * (sc ? __ldg(sc) : 1.0f);
   __shared__ float red[4][3][64];
   const int c = threadIdx.x & 63, ph = threadIdx.x >> 6;
   const int col = blockIdx.x * 64 + c;
@@ -331,21 +337,21 @@ __global__ void head_wgrad_kernel(const float* __restrict__ g, int q0, int nq, c
     for (int q = 0; q < nq; ++q) atomicAdd(gb + q, a * accb[q]);
 }
 cudaError_t launch_head_wgrad(const float* g, int q0, int nq, const __half* act, int N, int64_t P, float a, float* gW,
-                              float* gb, cudaStream_t s) {
+                              float* gb, cudaStream_t s, const float* sc) {
   if (P == 0) return cudaSuccess;
   dim3 grid(N / 64, static_cast<unsigned>((P + 2047) / 2048));
-  head_wgrad_kernel<<<grid, 256, 0, s>>>(g, q0, nq, act, N, P, a, gW, gb);
+  head_wgrad_kernel<<<grid, 256, 0, s>>>(g, q0, nq, act, N, P, a, gW, gb, sc);
   return cudaGetLastError();
 }
 
-__global__ void scale_f32_kernel(float* __restrict__ x, float a, int64_t n) {
+__global__ void scale_f32_kernel(float* __restrict__ x, float a, int64_t n, const float* __restrict__ sc) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i < n) x[i] *= a;
+  if (i < n) x[i] *= a * (sc ? __ldg(sc) : 1.0f);
 }
 
-cudaError_t launch_scale_f32(float* x, float a, int64_t n, cudaStream_t s) {
+cudaError_t launch_scale_f32(float* x, float a, int64_t n, cudaStream_t s, const float* sc) {
   if (n == 0) return cudaSuccess;
-  scale_f32_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(x, a, n);
+  scale_f32_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(x, a, n, sc);
   return cudaGetLastError();
 }
 

@@ -19,6 +19,7 @@ struct WgradParams {
   int ldc;
   int n_valid;       // columns < n_valid are written (padded encodings have 64 stored, 63 / 27 real columns)
   float scale;
+  const float* scale_dev;
   int m_tiles, n_tiles, splits;
   int kb_per_split;  // 64-row K blocks per split
   int kb_total;
@@ -164,15 +165,30 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mbar_wait(tfull0 + 8 * as, (it >> 1) & 1);
       tc_fence_after();
       float* crow = p.C + static_cast<size_t>(m0 + row) * p.ldc;
+      const float scale = p.scale * (p.scale_dev ? __ldg(p.scale_dev) : 1.0f);
+      // 16-byte vector reductions (red.global.add.v4.f32: a quarter of the atomic instructions) wherever this row's
+      // columns are 16-byte aligned — every plain W -> W layer (ldc = W) — scalar reductions otherwise (the layers whose
+      // reference weight has latent columns in front: ldc = 50 + W, 256 + 2W, ...)
+      const bool vec = ((reinterpret_cast<uintptr_t>(crow + n0) & 15) == 0) && ((p.ldc & 3) == 0);
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(tmem_base + lane_base + as * 256 + c * 32, v);
         tmem_ld_wait();
+        const int col0 = n0 + c * 32;
+        if (vec && col0 + 32 <= p.n_valid) {
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          const int col = n0 + c * 32 + e;
-          if (col < p.n_valid) atomicAdd(crow + col, __uint_as_float(v[e]) * p.scale);
+          for (int e = 0; e < 32; e += 4)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(crow + col0 + e),
+                         "f"(__uint_as_float(v[e]) * scale), "f"(__uint_as_float(v[e + 1]) * scale),
+                         "f"(__uint_as_float(v[e + 2]) * scale), "f"(__uint_as_float(v[e + 3]) * scale)
+                         : "memory");
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const int col = col0 + e;
+            if (col < p.n_valid) atomicAdd(crow + col, __uint_as_float(v[e]) * scale);
+          }
         }
       }
       tc_fence_before();
@@ -198,6 +214,7 @@ cudaError_t launch_wgrad_tc(const WgradLaunch& W, int num_sms, cudaStream_t stre
   p.ldc = W.ldc;
   p.n_valid = W.n_valid;
   p.scale = W.scale;
+  p.scale_dev = W.scale_dev;
   p.m_tiles = W.Mp / 128;
   p.n_tiles = W.Np / W.BN;
   p.kb_total = static_cast<int>(W.P / 64);

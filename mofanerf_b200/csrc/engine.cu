@@ -1508,7 +1508,7 @@ TrainWS carve_train(void* base, int64_t n, int S_c, int S_f, const Net& nc, cons
 // Backward of one pass through `net`: d_raw (loss-scaled) -> dX0/dV and latent gradients.
 // d_params (optional): fp32 gradient buffers in the canonical (weight, bias) order of mofa_b200_load_weights
 int run_backward(mofa_b200_ctx* c, Net& net, const TrainWS& t, const PassBufs& pb, int64_t P_rows, float inv_scale,
-                 float* const d_lat[4], float* const* d_params, cudaStream_t s) {
+                 float* const d_lat[4], float* const* d_params, cudaStream_t s, const float* inv_dev = nullptr) {
   const int64_t M = (P_rows + 127) / 128 * 128;
   std::vector<const Step*> dense;
   for (const Step& st : net.program)
@@ -1574,15 +1574,15 @@ int run_backward(mofa_b200_ctx* c, Net& net, const TrainWS& t, const PassBufs& p
       c->launches++;
     }
     if (L.fold_n > 0) {
-      CK(launch_fold_bwd(L.fold_w, L.fold_n, L.N, t.d_beff, inv_scale, d_lat[L.fold_lat], s));
+      CK(launch_fold_bwd(L.fold_w, L.fold_n, L.N, t.d_beff, inv_scale, d_lat[L.fold_lat], s, inv_dev));
       c->launches++;
     }
     if (d_params) {   // weight gradients: dW_seg += dZ^T · X_seg, db += colsum(dZ), latent columns += db (x) latent
       float* gW = d_params[2 * st.layer];
       float* gb = d_params[2 * st.layer + 1];
-      CK(launch_axpy_f32(t.d_beff, inv_scale, gb, L.N, s));
+      CK(launch_axpy_f32(t.d_beff, inv_scale, gb, L.N, s, inv_dev));
       if (L.fold_n > 0)
-        CK(launch_outer_add(t.d_beff, c->lat[L.fold_lat], L.N, L.fold_n, inv_scale, gW, L.in_ref, L.fold_c0, s));
+        CK(launch_outer_add(t.d_beff, c->lat[L.fold_lat], L.N, L.fold_n, inv_scale, gW, L.in_ref, L.fold_c0, s, inv_dev));
       for (int i = 0; i < L.nseg; ++i) {
         const __half* X = st.in_step[i] >= 0 ? pb.act[st.in_step[i]] : (st.in_step[i] == -1 ? pb.X0 : pb.V);
         WgradLaunch W;
@@ -1593,6 +1593,7 @@ int run_backward(mofa_b200_ctx* c, Net& net, const TrainWS& t, const PassBufs& p
         W.ldc = L.in_ref;
         W.n_valid = L.seg_kreal[i];
         W.scale = inv_scale;
+        W.scale_dev = inv_dev;
         W.Mp = L.N;
         W.BN = (L.K[i] % 256 == 0) ? 256 : 128;
         W.Np = (L.K[i] + W.BN - 1) / W.BN * W.BN;
@@ -1609,10 +1610,10 @@ int run_backward(mofa_b200_ctx* c, Net& net, const TrainWS& t, const PassBufs& p
       const Step& st = *dense[k];
       if (st.head == 1)
         CK(launch_head_wgrad(t.d_raw, 3, 1, pb.act[k], net.W, P_rows, inv_scale, d_params[2 * (n_dense + 0)],
-                             d_params[2 * (n_dense + 0) + 1], s));
+                             d_params[2 * (n_dense + 0) + 1], s, inv_dev));
       else if (st.head == 2)
         CK(launch_head_wgrad(t.d_raw, 0, 3, pb.act[k], net.W / 2, P_rows, inv_scale, d_params[2 * (n_dense + 1)],
-                             d_params[2 * (n_dense + 1) + 1], s));
+                             d_params[2 * (n_dense + 1) + 1], s, inv_dev));
     }
     c->launches += 2;
   }
@@ -1732,8 +1733,12 @@ int mofa_b200_render_rays_bwd(mofa_b200_ctx* c, const mofa_b200_bwd_args* a, voi
   if (t.total + slack > a->workspace_bytes) return fail("bwd: workspace too small");
   const int64_t n = a->n_rays;
   const int white = (a->flags & MOFA_FLAG_WHITE_BKGD) ? 1 : 0;
-  const float scale = a->loss_scale > 0.0f ? a->loss_scale : 1.0f;
+  // loss scale: a host value, or (loss_scale_dev) two floats in device memory {scale, 1 / scale} computed by the caller
+  // on the device — then nothing on this path ever waits for the GPU
+  const float* sdev = a->loss_scale_dev;
+  const float scale = sdev ? 1.0f : (a->loss_scale > 0.0f ? a->loss_scale : 1.0f);
   const float inv = 1.0f / scale;
+  const float* idev = sdev ? sdev + 1 : nullptr;
   float* d_lat[4] = {nullptr, a->d_expmod, a->d_shape, a->d_tex};
   CK(cudaMemsetAsync(a->d_rays, 0, sizeof(float) * 11 * n, s));
   CK(cudaMemsetAsync(a->d_shape, 0, sizeof(float) * kNShape, s));
@@ -1748,7 +1753,7 @@ int mofa_b200_render_rays_bwd(mofa_b200_ctx* c, const mofa_b200_bwd_args* a, voi
     const int S = ps == 1 ? S_f : S_c;
     const float* noise = ps == 1 ? a->noise_f : a->noise_c;
     CK(launch_composite_bwd(t.pass[ps].raw, t.pass[ps].z, a->rays, a->ray_stride, noise, g_rgb, g_acc, scale, n, S, white,
-                            t.d_raw, a->d_rays, s));
+                            t.d_raw, a->d_rays, s, sdev));
     c->launches++;
     {
       const int64_t rows = n * S, pad = (rows + 127) / 128 * 128 - rows;
@@ -1757,11 +1762,11 @@ int mofa_b200_render_rays_bwd(mofa_b200_ctx* c, const mofa_b200_bwd_args* a, voi
     float* const* dp = (&net == &nc) ? a->d_params_coarse : a->d_params_fine;
     if (dp && (&net == &nc ? a->n_params_coarse : a->n_params_fine) != 2 * (n_dense_steps(net) + 2))
       return fail("bwd: d_params has the wrong number of tensors");
-    if (run_backward(c, net, t, t.pass[ps], n * S, inv, d_lat, dp, s)) return 1;
+    if (run_backward(c, net, t, t.pass[ps], n * S, inv, d_lat, dp, s, idev)) return 1;
     CK(launch_pe_bwd(a->rays, a->ray_stride, t.pass[ps].z, t.dX0, t.dV, 128, n, S, a->d_rays, s));
     c->launches++;
   }
-  CK(launch_scale_f32(a->d_rays, inv, 11 * n, s));
+  CK(launch_scale_f32(a->d_rays, inv, 11 * n, s, idev));
   c->launches++;
   return 0;
 }
@@ -1792,7 +1797,7 @@ int mofa_b200_wgrad(mofa_b200_ctx* c, const void* A, int Mp, const void* B, int 
     memset(&W, 0, sizeof(W));
     if (make_tmap_2d(c, &W.tmA, A, (uint64_t)P, (uint64_t)Mp, (uint64_t)Mp, 64)) return 1;
     if (make_tmap_2d(c, &W.tmB, B, (uint64_t)P, (uint64_t)Kb, (uint64_t)Kb, 64)) return 1;
-    W.C = C; W.ldc = ldc; W.n_valid = n_valid; W.scale = scale; W.Mp = Mp;
+    W.C = C; W.ldc = ldc; W.n_valid = n_valid; W.scale = scale; W.scale_dev = nullptr; W.Mp = Mp;
     W.BN = (Kb % 256 == 0) ? 256 : 128;
     W.Np = (Kb + W.BN - 1) / W.BN * W.BN;
     W.P = P;

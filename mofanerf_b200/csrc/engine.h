@@ -179,22 +179,23 @@ constexpr int kChainSlabMb = 56;          // m-blocks per slab: 56 x 4 n-tiles =
 // ---- backward pass (backward.cu) ----------------------------------------------------------------
 cudaError_t launch_composite_bwd(const float* raw, const float* z, const float* rays, int stride, const float* noise,
                                  const float* d_rgb, const float* d_acc, float gscale, int64_t n, int S,
-                                 int white_bkgd, float* d_raw, float* d_rays, cudaStream_t s);
+                                 int white_bkgd, float* d_raw, float* d_rays, cudaStream_t s, const float* sc = nullptr);
+// (every scalar factor below is multiplied by *sc when sc != nullptr: a device-resident loss scale / its inverse)
 cudaError_t launch_view_head_bwd(const float* d_raw, const float* w_rgb, const __half* HV, int Nh, int64_t P,
                                  __half* dZ, cudaStream_t s);
 cudaError_t launch_colsum(const __half* dZ, int N, int64_t P, float* out, cudaStream_t s);
 cudaError_t launch_fold_bwd(const float* fold_w, int nlat, int N, const float* d_beff, float inv_scale, float* d_lat,
-                            cudaStream_t s);
+                            cudaStream_t s, const float* sc = nullptr);
 cudaError_t launch_pe_bwd(const float* rays, int stride, const float* z, const __half* dX0, const __half* dV, int ld,
                           int64_t n, int S, float* d_rays, cudaStream_t s);
 cudaError_t launch_pack_weight_t(const float* src, int ld, int c0, int K, int krows_pad, int N, __half* dst,
                                  cudaStream_t s);
-cudaError_t launch_scale_f32(float* x, float a, int64_t n, cudaStream_t s);
-cudaError_t launch_axpy_f32(const float* x, float a, float* y, int n, cudaStream_t s);
+cudaError_t launch_scale_f32(float* x, float a, int64_t n, cudaStream_t s, const float* sc = nullptr);
+cudaError_t launch_axpy_f32(const float* x, float a, float* y, int n, cudaStream_t s, const float* sc = nullptr);
 cudaError_t launch_outer_add(const float* u, const float* v, int rows, int cols, float a, float* G, int ld, int c0,
-                             cudaStream_t s);
+                             cudaStream_t s, const float* sc = nullptr);
 cudaError_t launch_head_wgrad(const float* g, int q0, int nq, const __half* act, int N, int64_t P, float a, float* gW,
-                              float* gb, cudaStream_t s);
+                              float* gb, cudaStream_t s, const float* sc = nullptr);
 
 // ---- weight-gradient GEMM (dense_wgrad.cu): C[Mp, :] += scale * A^T B, reduction over the P rows of A [P,Mp], B [P,Np]
 struct WgradLaunch {
@@ -204,6 +205,7 @@ struct WgradLaunch {
   int ldc;
   int n_valid;       // real columns of B
   float scale;
+  const float* scale_dev;   // optional device-resident factor multiplied into `scale`
   int Mp;            // multiple of 128
   int Np;            // multiple of BN (columns beyond the tensor are zero-filled by TMA)
   int BN;            // 128 or 256

@@ -202,6 +202,7 @@ class Engine:
                         fine_net: int, white_bkgd: bool, lindisp: bool, d_rgb=None, d_acc=None, d_rgb0=None,
                         d_acc0=None, loss_scale: float = 1.0, param_grads=None):
         """Backward of a training-mode render_rays: returns (d_rays [n,11], d_shape [50], d_expmod [30], d_tex [256]).
+        loss_scale: a Python float, or a device tensor {scale, 1/scale} (no host synchronisation).
         param_grads: optional (coarse_list, fine_list) of zero-initialised fp32 tensors shaped like the canonical
         (weight, bias) parameter lists; weight gradients are accumulated into them (training)."""
         rays, ws = saved["_rays"], saved["_train_ws"]
@@ -220,7 +221,11 @@ class Engine:
             a.run_fine, a.fine_net = int(bool(run_fine)), int(fine_net)
             a.noise_c, a.noise_f = _ptr(noise_c), _ptr(noise_f)
             a.d_rgb, a.d_acc, a.d_rgb0, a.d_acc0 = [_ptr(x) for x in g]
-            a.loss_scale = float(loss_scale)
+            if torch.is_tensor(loss_scale):     # device-resident {scale, 1/scale}: no host round trip
+                loss_scale = loss_scale.to(device=dev, dtype=torch.float32).contiguous()
+                a.loss_scale, a.loss_scale_dev = 1.0, loss_scale.data_ptr()
+            else:
+                a.loss_scale = float(loss_scale)
             a.d_rays, a.d_shape, a.d_expmod, a.d_tex = d_rays.data_ptr(), d_shape.data_ptr(), d_exp.data_ptr(), d_tex.data_ptr()
             keep = []
             if param_grads is not None:
@@ -233,7 +238,7 @@ class Engine:
                     setattr(a, f"n_params_{name}", len(lst))
             a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
             _lib.check(self.lib.mofa_b200_render_rays_bwd(self._h, C.byref(a), self._stream()))
-        self._keep["bwd"] = g
+        self._keep["bwd"] = (g, loss_scale)
         return d_rays, d_shape, d_exp, d_tex
 
     def run_network(self, which: int, pts: torch.Tensor, viewdirs: torch.Tensor, gemm_simt: bool = False) -> torch.Tensor:

@@ -34,8 +34,8 @@ def test_render_args_struct_matches_header_layout():
     from mofanerf_b200 import _lib
     # 2*u32, ptr, i64, 6*i32, 2*f32, u64, 14 pointers, ptr, size_t  (LP64)
     assert ctypes.sizeof(_lib.RenderArgs) == 8 + 8 + 8 + 24 + 8 + 8 + 14 * 8 + 8 + 8
-    # 2*u32, ptr, i64, 6*i32, 6 pointers, 2*f32, 4 pointers, ptr, size_t
-    assert ctypes.sizeof(_lib.BwdArgs) == 8 + 8 + 8 + 24 + 6 * 8 + 8 + 4 * 8 + 2 * 8 + 8 + 8 + 8
+    # 2*u32, ptr, i64, 6*i32, 6 pointers, 2*f32, 4 pointers, 2 pointers, 2*i32, ptr, size_t, ptr (loss_scale_dev)
+    assert ctypes.sizeof(_lib.BwdArgs) == 8 + 8 + 8 + 24 + 6 * 8 + 8 + 4 * 8 + 2 * 8 + 8 + 8 + 8 + 8
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")

@@ -276,6 +276,60 @@ def test_training_weight_gradients_exact_on_affine_net(n, S, Ni):
     print(f"[parity] affine-net weight gradients: worst relative error {worst:.2e} over {len(ref)} tensors")
 
 
+def test_training_weight_gradients_random_init_vs_fp16_emulated_oracle():
+    """Weight gradients on RANDOM-INIT nets (ReLU masks active) against autograd through the oracle with the engine's
+    rounding emulated (tests/fp16_emulation.py) at the engine's own fine depths.  As for the fitting gradients the
+    residual is ReLU-mask flips from 1e-4-level forward differences, so the bound is rel <= 0.2, cosine >= 0.98 per
+    tensor over the tensors that carry signal (a sign / missing-term / wrong-layout bug gives cosine ~ 0)."""
+    from mofanerf_b200 import B200Renderer
+    from mofanerf_b200.rays import pack_rays
+    from tests.fp16_emulation import nerf_forward_fp16
+    meta, inp, _ = load_case("small_w256")
+    c, f, s = build_case_nets(meta)
+    n, S, Ni = 40, 64, 64
+    ro, rd = inp["rays_o"][:n].clone(), inp["rays_d"][:n].clone()
+    g = torch.Generator().manual_seed(9)
+    w_rgb, w_rgb0 = torch.randn(n, 3, generator=g), torch.randn(n, 3, generator=g)
+    r = B200Renderer(expCodesLen=30).to(DEV)
+    r.idSpecificMod.load_state_dict(s.state_dict())
+    for m in (c, f):
+        m.train()
+        m.zero_grad()
+    c.to(DEV); f.to(DEV)
+    vd = rd / torch.norm(rd, dim=-1, keepdim=True)
+    r.shapeCodes, r.expType, r.decoding_texCodes = inp["shape"].to(DEV), 20, inp["tex"].to(DEV)
+    r.expCodes_Sigma.append(inp["exp"].to(DEV))
+    r.rays = pack_rays(ro, rd, 8.0, 26.0, vd).to(DEV)
+    ret = r.batchify_rays(1 << 20, network_fn=c, network_fine=f, N_samples=S, N_importance=Ni, perturb=0.0,
+                          raw_noise_std=0.0, want_aux=True)
+    ((ret["rgb_map"] * w_rgb.to(DEV)).sum() + (ret["rgb0"] * w_rgb0.to(DEV)).sum()).backward()
+    got = {("c", k): p.grad.detach().cpu() for k, p in c.named_parameters()}
+    got.update({("f", k): p.grad.detach().cpu() for k, p in f.named_parameters()})
+    z_fine = ret["z_vals"].detach().cpu()
+    c.cpu(); f.cpu()
+    for m in (c, f):
+        m.zero_grad()
+    rays = O.make_ray_batch(ro, rd, 8.0, 26.0)
+    em = O.expression_mod(s, inp["shape"], inp["exp"])
+    out = O.render_rays(rays, c, f, inp["shape"], em, inp["tex"], N_samples=S, N_importance=Ni, z_fine_override=z_fine,
+                        forward_fn=nerf_forward_fp16)
+    ((out["rgb_map"] * w_rgb).sum() + (out["rgb0"] * w_rgb0).sum()).backward()
+    worst_rel, worst_cos, checked = 0.0, 1.0, 0
+    for tag, net in (("c", c), ("f", f)):
+        for k, p in net.named_parameters():
+            rf, gr = p.grad.double().flatten(), got[(tag, k)].double().flatten()
+            assert bool(torch.isfinite(gr).all()), f"{tag}:{k}"
+            if rf.norm().item() < 1e-9:
+                continue
+            rel = ((gr - rf).norm() / rf.norm()).item()
+            cs = (torch.dot(gr, rf) / (gr.norm() * rf.norm()).clamp_min(1e-30)).item()
+            worst_rel, worst_cos, checked = max(worst_rel, rel), min(worst_cos, cs), checked + 1
+            assert rel <= 0.2 and cs >= 0.98, f"weight gradient {tag}:{k}: rel {rel:.3e} cos {cs:.5f}"
+    print(f"[parity] random-init weight gradients vs fp16-emulated oracle: worst rel {worst_rel:.2e}, worst cos {worst_cos:.5f} "
+          f"over {checked} tensors")
+    assert checked >= 90
+
+
 def test_training_step_through_render_updates_all_parameter_groups():
     """run_train.py:333-357 in miniature: render() (texture encoder + expression slot), stratified jitter (perturb=1,
     in-kernel Philox), MSE on rgb + rgb0, one Adam over NeRF weights + texEncoder + idSpecificMod + expression codes.
