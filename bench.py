@@ -285,10 +285,19 @@ def run_fit_workload(args, train=False):
     """BASELINE config #3: one run_fit.py fitting iteration = 1024 random rays, FULL pipeline, forward + backward to the
     latent codes and the pose, L1 loss, three Adam steps (run_fit.py:281-313).  Not the headline metric: printed as its own
     JSON line for the record."""
-    dev = torch.device("cuda", 0)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:      # data-parallel training (SURVEY §8 f2): every rank draws its own rays, gradients are averaged
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
     import __graft_entry__
     __graft_entry__.build()
     from mofanerf_b200 import B200Renderer, nets
+    from mofanerf_b200.distributed import allreduce_gradients
     coarse, fine, style = nets.build_nets(0, device=dev)
     coarse.train(train)
     fine.train(train)
@@ -296,7 +305,7 @@ def run_fit_workload(args, train=False):
     r = B200Renderer(expCodesLen=30).to(dev)
     r.idSpecificMod.load_state_dict(style.state_dict())
     n = 1024
-    g = torch.Generator().manual_seed(0)
+    g = torch.Generator().manual_seed(rank)
     kw = dict(near=8.0, far=26.0, use_viewdirs=True, ndc=False, network_fn=coarse, network_fine=fine,
               N_samples=args.n_samples, N_importance=args.n_importance, perturb=0.0, raw_noise_std=0.0)
     shape = shape.to(dev).requires_grad_(True)
@@ -306,8 +315,11 @@ def run_fit_workload(args, train=False):
     light = torch.ones(1, device=dev, requires_grad=True)
     opts = [torch.optim.Adam([light, pose_delta], lr=2e-3), torch.optim.Adam([tex], lr=2e-3),
             torch.optim.Adam([exp, shape], lr=4e-3)]
+    all_params = []
     if train:   # run_train.py: one Adam over the NeRF weights (+ renderer parameters)
-        opts = [torch.optim.Adam(list(coarse.parameters()) + list(fine.parameters()) + r.grad_parameter(), lr=5e-5)]
+        all_params = list(coarse.parameters()) + list(fine.parameters()) + r.grad_parameter()
+        opts = [torch.optim.Adam(all_params, lr=5e-5)]
+    ar_ev = []
     target = torch.rand(n, 3, device=dev)
     ro_d, rd_d = ro.to(dev), rd.to(dev)
     l1 = torch.nn.L1Loss()
@@ -329,11 +341,20 @@ def run_fit_workload(args, train=False):
         for o in opts:
             o.zero_grad()
         loss.backward()
+        if world > 1 and train:   # the one exchange step of the path: bucketed NCCL all-reduce of param.grad
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            allreduce_gradients(all_params)
+            e1.record()
+            ar_ev.append((e0, e1))
         for o in opts:
             o.step()
 
     for _ in range(max(3, args.warmup)):
         step()
+    ar_ev.clear()
+    if world > 1:
+        dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     iters = max(10, args.steps)
@@ -343,6 +364,15 @@ def run_fit_workload(args, train=False):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
+    ar_ms = sum(a.elapsed_time(b) for a, b in ar_ev) / max(1, len(ar_ev)) if ar_ev else 0.0
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        if rank != 0:
+            dist.barrier()
+            dist.destroy_process_group()
+            return
     fwd = n * (args.n_samples * FLOP_COARSE_PT + (args.n_samples + args.n_importance) * FLOP_FINE_PT)
     bwd = n * (args.n_samples + args.n_importance) * FLOP_FINE_PT       # dX only, fine pass only (rgb0 is not in the loss)
     name = "train iterations/s (run_train.py: 1024 rays, 64+128 samples, fwd+bwd incl. weight gradients+Adam)" if train else \
@@ -350,9 +380,16 @@ def run_fit_workload(args, train=False):
     if train:   # dX + dW for both passes (rgb0 is in the loss)
         bwd = 2 * fwd
     print(json.dumps({"metric": name, "value": 1e3 / ms,
-                      "unit": "it/s", "ms_per_iter": ms, "rays_per_s": n * 1e3 / ms, "n_gpus": 1,
-                      "algorithmic_tflops": (fwd + bwd) / (ms / 1e3) / 1e12, "data": "synthetic",
-                      "config": {"workload": ("run_train.py step" if train else "BASELINE config #3: fitting loop") + ", N_rand=1024, FULL, 1 x B200"}}), flush=True)
+                      "unit": "it/s", "ms_per_iter": ms, "rays_per_s": world * n * 1e3 / ms, "n_gpus": world,
+                      "algorithmic_tflops": world * (fwd + bwd) / (ms / 1e3) / 1e12, "data": "synthetic",
+                      "gradient_allreduce_ms": ar_ms if world > 1 and train else None,
+                      "config": {"workload": ("run_train.py step" if train else "BASELINE config #3: fitting loop") +
+                                 f", N_rand=1024 per rank, FULL, {world} x B200" +
+                                 (", data parallel: bucketed NCCL all-reduce of 29 M fp32 gradients per step" if world > 1 and train else "")}}),
+          flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 def run_image_workload(args, rank, world, local_rank):

@@ -99,5 +99,7 @@ __device__ __forceinline__ void mbar_arrive_cluster_release(uint32_t cluster_add
 // branch so that ptxas allocates the two regions separately).
 __device__ __forceinline__ void setmaxnreg_dec_40() { asm volatile("setmaxnreg.dec.sync.aligned.u32 40;"); }
 __device__ __forceinline__ void setmaxnreg_inc_232() { asm volatile("setmaxnreg.inc.sync.aligned.u32 232;"); }
+// 512-thread CTAs (one 128-thread producer/MMA warpgroup + three epilogue warpgroups): 128*40 + 384*152 = 63488 <= 65536
+__device__ __forceinline__ void setmaxnreg_inc_152() { asm volatile("setmaxnreg.inc.sync.aligned.u32 152;"); }
 
 }  // namespace mofa
