@@ -410,7 +410,7 @@ def run_image_workload(args, rank, world, local_rank):
     __graft_entry__.build()
     from mofanerf_b200 import B200Renderer, nets
     from mofanerf_b200.rays import pose_spherical
-    from mofanerf_b200.renderer import AsyncImageSink
+    from mofanerf_b200.renderer import AsyncImageSink, wait_for_images
 
     sweep = args.workload == "sweep20"
     H = W = (args.H if sweep else 256)
@@ -420,6 +420,7 @@ def run_image_workload(args, rank, world, local_rank):
     r = B200Renderer(expCodesLen=30).to(dev)
     r.idSpecificMod.load_state_dict(style.state_dict())
     r.shard_rays = world > 1
+    r.async_png = True         # bulk-job mode: PNG files are written behind the renderer; the timed step ends with wait_for_images()
     focal = 1200.0 * H / 512.0
     K = np.array([[focal, 0, 0.5 * W], [0, focal, 0.5 * H], [0, 0, 1]])
     kw = dict(near=8.0, far=26.0, use_viewdirs=True, ndc=False, network_fn=coarse, network_fine=fine,
@@ -469,20 +470,21 @@ def run_image_workload(args, rank, world, local_rank):
                                            expCodes=r.expCodes_Sigma[e], **kw)[0]
                     sink.submit([rgb], os.path.join(tmp, f"rigging_{k:03d}.png") if rank == 0 else None)
                 sink.results()
-                sink.close()
+                sink.wait_files()                 # the step ends when the PNG files are on disk
                 png_bytes[0] = sink.png_bytes
             else:     # render_path per image, exactly as render_refine_trainSet.py:295 calls it (one pose per call)
                 import contextlib
                 import io
-                total = 0
+                sinks = []
                 for i in range(n_img):
                     uv = uv_h[uv_idx[i]].unsqueeze(0).to(dev, non_blocking=True)      # host UV map -> device, per image
                     with contextlib.redirect_stdout(io.StringIO()):
                         r.render_path(poses_h[i:i + 1], [H, W, focal], K, 1 << 30, kw, uvMap=uv,
                                       expType=[exp_slots[i]], savedir=tmp if rank == 0 else None,
                                       shapeCodes=shapes_img[i:i + 1].to(dev), name=f"img_{i:05d}" if rank == 0 else None)
-                    total += r.last_sink.png_bytes
-                png_bytes[0] = total
+                    sinks.append(r.last_sink)
+                wait_for_images()                 # the step ends when every PNG file is on disk
+                png_bytes[0] = sum(sk.png_bytes for sk in sinks)
 
     def timed(fn, steps):
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
@@ -562,8 +564,8 @@ def run_image_workload(args, rank, world, local_rank):
                     "h2d_bytes_per_step": 0 if sweep else int(n_img * 512 * 512 * 3 * 4),
                     "d2h_bytes_per_step": int(n_img * H * W * (3 if sweep else 4) * 4), "png_bytes_per_step": int(png_bytes[0]),
                     "api": ("render_fitting(c2w=...) per expression + AsyncImageSink (device->host copy and PNG on a worker thread)"
-                            if sweep else "render_path(...) per image: UV map host->device, texture encoder on a side stream, "
-                            "device->host copy and PNG on a worker thread")},
+                            if sweep else "render_path(...) per image (MOFA_B200_ASYNC_PNG mode): UV map host->device, texture encoder on a side "
+                            "stream, device->host copy per call, PNG files by background writers, all on disk before the step ends")},
             "gpu_launches": int(launches),
             "whole_step_tflops": flop / world / (ms_dev / 1e3) / 1e12}
     if mg_check is not None:

@@ -8,6 +8,6 @@ Public surface:
 """
 from . import nets  # noqa: F401
 from .engine import Engine, get_engine  # noqa: F401
-from .renderer import B200Renderer, install  # noqa: F401
+from .renderer import B200Renderer, install, wait_for_images  # noqa: F401
 
-__all__ = ["B200Renderer", "install", "Engine", "get_engine", "nets"]
+__all__ = ["B200Renderer", "install", "wait_for_images", "Engine", "get_engine", "nets"]

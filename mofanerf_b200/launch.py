@@ -158,6 +158,9 @@ def main(argv=None) -> None:
     ap.add_argument("--reference-root", default=None, help="reference tree (default: the script's directory)")
     ap.add_argument("--shim-missing", action="store_true", help="stand-ins for missing imageio / configargparse / ...")
     ap.add_argument("--shard", action="store_true", help="ray-shard every image across the ranks (MOFA_B200_SHARD=1)")
+    ap.add_argument("--async-png", action="store_true",
+                    help="render_path returns when the frames are in host memory; PNG files are written in the background "
+                         "(MOFA_B200_ASYNC_PNG=1) and joined at exit")
     ap.add_argument("--no-chdir", action="store_true", help="do not change into the reference tree")
     ap.add_argument("script")
     ap.add_argument("script_args", nargs=argparse.REMAINDER)
@@ -191,6 +194,8 @@ def main(argv=None) -> None:
                                     **({"device_id": torch.device("cuda", local_rank)} if have_gpu else {}))
     if a.shard:
         os.environ["MOFA_B200_SHARD"] = "1"
+    if a.async_png:
+        os.environ["MOFA_B200_ASYNC_PNG"] = "1"
 
     sys.argv = [script] + list(a.script_args)
     runpy.run_path(script, run_name="__main__")

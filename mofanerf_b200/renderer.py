@@ -52,17 +52,45 @@ class lossesLog:
         return loss
 
 
+_png_pool = None
+_png_jobs = []
+_png_lock = threading.Lock()
+
+
+def _png_submit(fn, *args):
+    """PNG files are encoded and written by a process-wide worker pool: a caller of render_path gets its arrays back as
+    soon as the device->host copy has landed, the file follows shortly after (wait_for_images() / interpreter exit)."""
+    global _png_pool
+    with _png_lock:
+        if _png_pool is None:
+            import atexit
+            _png_pool = ThreadPoolExecutor(max_workers=4)
+            atexit.register(wait_for_images)
+        job = _png_pool.submit(fn, *args)
+        _png_jobs.append(job)
+    return job
+
+
+def wait_for_images() -> None:
+    """Block until every PNG handed to the background writers is on disk (re-raises a writer's exception)."""
+    with _png_lock:
+        jobs = list(_png_jobs)
+        del _png_jobs[:]
+    for j in jobs:
+        j.result()
+
+
 class AsyncImageSink:
     """Device -> host copy and PNG encoding of finished frames OFF the rendering path (the reference does
     `rgb.cpu().numpy()` + imageio.imwrite synchronously after every frame, models/render_class.py:224-233).
 
     submit() enqueues, on the rendering stream, an asynchronous copy of the frame into pinned host memory and records an
-    event; a worker thread waits for that event only, converts to 8 bit and writes the PNG, while the caller goes on
-    enqueueing the next frame.  results() joins everything and returns the float frames in submission order."""
+    event; the caller goes on enqueueing the next frame.  results() waits for the copies (not for the files) and returns
+    the float frames in submission order; each frame's 8-bit conversion + PNG write runs on the background writers as
+    soon as its copy has landed (wait_for_images() joins them; png_bytes is final after that)."""
 
-    def __init__(self, workers: int = 2):
-        self._pool = ThreadPoolExecutor(max_workers=workers)
-        self._jobs = []
+    def __init__(self):
+        self._frames = []
         self.png_bytes = 0
         self._lock = threading.Lock()
 
@@ -76,25 +104,31 @@ class AsyncImageSink:
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream(tensors[0].device))
 
-        def finish():
+        def write():
             if ev is not None:
                 ev.synchronize()
-            arrays = [h.numpy() for h in host]
-            if filename is not None:
-                _imwrite(filename, to8b(arrays[0]))
-                with self._lock:
-                    self.png_bytes += os.path.getsize(filename)
-            return arrays
+            _imwrite(filename, to8b(host[0].numpy()))
+            with self._lock:
+                self.png_bytes += os.path.getsize(filename)
 
-        self._jobs.append(self._pool.submit(finish))
+        job = _png_submit(write) if filename is not None else None
+        self._frames.append((host, ev, job))
 
     def results(self):
-        out = [j.result() for j in self._jobs]
-        self._jobs = []
+        out = []
+        for host, ev, _ in self._frames:
+            if ev is not None:
+                ev.synchronize()
+            out.append([h.numpy() for h in host])
         return out
 
+    def wait_files(self):
+        for _, _, job in self._frames:
+            if job is not None:
+                job.result()
+
     def close(self):
-        self._pool.shutdown(wait=True)
+        pass
 
 
 def _needs_grad(*tensors) -> bool:
@@ -124,6 +158,10 @@ class B200Renderer(torch.nn.Module):
             latent.requires_grad = True
         self._engine: Optional[Engine] = None
         self.shard_rays = os.environ.get("MOFA_B200_SHARD", "0") == "1"
+        # render_path returns once the frames are in host memory and leaves the PNG files to the background writers
+        # (bulk jobs such as render_refine_trainSet.py; mofanerf_b200.wait_for_images() joins them).  Default: the files
+        # are on disk when render_path returns, as in the reference.
+        self.async_png = os.environ.get("MOFA_B200_ASYNC_PNG", "0") == "1"
         self.seed = 0
         self._call = 0
         self._local_range = None
@@ -385,6 +423,7 @@ class B200Renderer(torch.nn.Module):
         t = time.time()
         if savedir is not None:
             filename = os.path.join(savedir, '{}.png'.format(name))
+            wait_for_images()                      # a frame still being written by the background writers counts
             if os.path.exists(filename):
                 print("exists")
                 return 0, 0
@@ -422,7 +461,8 @@ class B200Renderer(torch.nn.Module):
                 fn = os.path.join(savedir, '{}.png'.format(name) if name is not None else '{:03d}.png'.format(i))
             sink.submit([rgb, disp], fn)
         frames = sink.results()
-        sink.close()
+        if not self.async_png:
+            sink.wait_files()
         rgbs = [f[0] for f in frames]
         disps = [f[1] for f in frames]
         return np.stack(rgbs, 0), np.stack(disps, 0)
