@@ -37,6 +37,7 @@ def neutralise_device_pin(local_rank: int) -> bool:
     torch.cuda.set_device(local_rank)
     torch.cuda.init()
     torch.zeros(1, device=f"cuda:{local_rank}")      # forces context creation on the device
+    torch.cuda.device_count()                         # cached by torch once CUDA is initialised: later calls do not re-read the env
     return True
 
 
