@@ -171,3 +171,35 @@ def test_packed_weight_cache_round_trip(tmp_path):
     assert not torch.equal(d.render_rays(rays, 64, 64)["rgb_map"], ref["rgb_map"])
     for e in (a, b, c, d):
         e.close()
+
+
+def test_fine_chain_kernel_on_a_512_wide_net():
+    """The chain kernel also takes W = 512 nets (two n-tiles per layer, one for the view layer).  Against one launch per
+    layer the view layer's rgb head is summed in a different order (pair tile with two epilogue groups instead of a
+    single-CTA tile), so the comparison is to fp32 rounding, not bit for bit."""
+    from mofanerf_b200 import nets
+    from mofanerf_b200.engine import Engine
+    coarse, fine, _ = nets.build_nets(2, W_f=512, device=DEV)
+    g = torch.Generator().manual_seed(8)
+    shape, tex, em = torch.randn(50, generator=g) * 0.034, 0.14 + 0.26 * torch.randn(256, generator=g), torch.rand(30, generator=g)
+    n = 150
+    rd = torch.nn.functional.normalize(torch.randn(n, 3, generator=g) * 0.1 + torch.tensor([0.0, 0.0, -1.0]), dim=-1)
+    rays = torch.cat([torch.zeros(n, 3) + torch.tensor([0.0, 0.0, 16.0]), rd, torch.full((n, 1), 8.0), torch.full((n, 1), 26.0),
+                      rd, torch.zeros(n, 1)], -1).to(DEV)
+    outs = {}
+    for mode in ("chain", "per_layer"):
+        if mode == "per_layer":
+            os.environ["MOFA_B200_FINE_PER_LAYER"] = "1"
+        try:
+            eng = Engine(DEV)
+        finally:
+            os.environ.pop("MOFA_B200_FINE_PER_LAYER", None)
+        eng.load_network(0, coarse)
+        eng.load_network(1, fine)
+        eng.set_latents(shape, em, tex)
+        outs[mode] = {k: v.clone() for k, v in eng.render_rays(rays, 64, 64, retraw=True).items()}
+        torch.cuda.synchronize()
+        eng.close()
+    assert torch.equal(outs["chain"]["raw"][..., 3], outs["per_layer"]["raw"][..., 3])          # sigma: same tiles, same order
+    assert (outs["chain"]["raw"] - outs["per_layer"]["raw"]).abs().max().item() <= 1e-4
+    assert (outs["chain"]["rgb_map"] - outs["per_layer"]["rgb_map"]).abs().max().item() <= 1e-5
