@@ -44,3 +44,23 @@ def test_install_swaps_renderer_and_create_nerf_uses_it(tmp_path):
         assert len(render.expCodes_Sigma) == 20 and render.expCodes_Sigma[0].shape == (1, 30)
     finally:
         rc.myRenderer = orig
+
+
+def test_host_ray_helpers_match_the_reference_functions():
+    """rays.get_rays / ndc_rays / pose_spherical (host path kept for NDC, explicit rays, c2w_staticcam) against the
+    reference's own functions on fresh inputs (tools/run_nerf_helpers.py:153-199, tools/load_facescape.py:33-38)."""
+    import numpy as np
+    ref = ref_loader.load()
+    from mofanerf_b200 import rays as R
+    import tools.load_facescape as lf
+    H, W, focal = 12, 9, 30.0
+    K = np.array([[focal, 0, 0.5 * W], [0, focal, 0.5 * H], [0, 0, 1]])
+    for angle in (-70.0, 15.0):
+        c2w = lf.pose_spherical(angle, -10.0, 4.0)
+        assert torch.equal(R.pose_spherical(angle, -10.0, 4.0), c2w)
+        ro_r, rd_r = ref.helpers.get_rays(H, W, K, c2w[:3, :4])
+        ro, rd = R.get_rays(H, W, K, c2w[:3, :4])
+        assert torch.equal(ro, ro_r) and torch.equal(rd, rd_r)
+        a = ref.helpers.ndc_rays(H, W, focal, 1.0, ro_r, rd_r)
+        b = R.ndc_rays(H, W, focal, 1.0, ro, rd)
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
