@@ -76,6 +76,10 @@ struct Layer {
   __half* wlo[2] = {nullptr, nullptr};
   CUtensorMap tmS_hi[2];         // box rows = N / 2
   CUtensorMap tmS_lo[2];
+  // opt-in FP8 variant (MOFA_B200_FP8; plain W -> W layers of a wide net only): e4m3 image, per-row scale / activation scale
+  uint8_t* w8 = nullptr;
+  float* colscale8 = nullptr;
+  CUtensorMap tmB8;              // box 128 rows x 128 bytes
 };
 
 struct Step {
@@ -120,6 +124,8 @@ struct mofa_b200_ctx {
   bool latents_set = false;
   bool pair_kernel = true;       // cta_group::2 kernel for N % 256 == 0 (MOFA_B200_DENSE_1CTA=1 disables)
   bool fused_coarse = true;      // one persistent kernel for a W == 256 net (MOFA_B200_NO_FUSED_COARSE=1 disables)
+  int fp8_layers = 0;            // MOFA_B200_FP8=n: the first n plain W -> W layers of a wide net run with e4m3 operands
+                                 // (1 = all of them).  NOT the default: fails the stated tolerance (profiles/r02_fp8_parity_study.json)
   bool importing = false;        // load_weights is being driven by mofa_b200_import_packed: build the structure, read no sources
   bool chain_fine = true;        // all dense layers of a W >= 512 net in one persistent launch, activations L2-resident
                                  // (fine_chain.cu); MOFA_B200_FINE_PER_LAYER=1 selects one launch per layer (round 1)
@@ -157,6 +163,22 @@ int make_tmap_2d(mofa_b200_ctx* c, CUtensorMap* m, const void* ptr, uint64_t row
   if (r != CUDA_SUCCESS)
     return fail("cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu pitch=%llu box_rows=%u ptr=%p", (int)r,
                 (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)pitch, box_rows, ptr);
+  return 0;
+}
+
+// 8-bit (e4m3) operand / output maps of the FP8 variant: bytes as elements.  box_cols = 128 (operands, SWIZZLE_128B) or 32
+// (the chain kernel's half-block stores, no swizzle)
+int make_tmap_u8(mofa_b200_ctx* c, CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t pitch,
+                 uint32_t box_rows, uint32_t box_cols) {
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {pitch};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = c->encode(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         box_cols == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled (u8) failed (%d)", (int)r);
   return 0;
 }
 
@@ -229,6 +251,14 @@ int build_layer(mofa_b200_ctx* c, Net& net, const LayerSpec& sp, const float* w,
     }
     if (make_tmap_2d(c, &L.tmBt[i], L.wt[i], L.rows_t[i], sp.N, sp.N, L.BN_t[i])) return 1;
     if (make_tmap_2d(c, &L.tmBt2[i], L.wt[i], L.rows_t[i], sp.N, sp.N, 128)) return 1;
+  }
+  if (c->fp8_layers > 0 && !imp && net.W >= 512 && sp.nseg == 1 && sp.fold_n == 0 && sp.seg_k[0] == net.W && sp.N == net.W) {
+    // (not part of the packed blob: the FP8 variant is a measurement mode)
+    if (dev_alloc(net, reinterpret_cast<void**>(&L.w8), (size_t)sp.N * sp.seg_k[0])) return 1;
+    if (dev_alloc(net, reinterpret_cast<void**>(&L.colscale8), sizeof(float) * sp.N)) return 1;
+    CK(launch_pack_weight_fp8(w, sp.in_total, sp.seg_c0[0], sp.seg_k[0], sp.N, 8.0f, L.w8, L.colscale8, s));
+    c->launches++;
+    if (make_tmap_u8(c, &L.tmB8, L.w8, sp.N, sp.seg_k[0], sp.seg_k[0], 128, 128)) return 1;
   }
   if (dev_alloc_data(net, reinterpret_cast<void**>(&L.bias_raw), sizeof(float) * sp.N)) return 1;
   if (!imp) CK(cudaMemcpyAsync(L.bias_raw, b, sizeof(float) * sp.N, cudaMemcpyDeviceToDevice, s));
@@ -394,7 +424,7 @@ struct ViewSrc {
   int rows_per_group;
 };
 
-constexpr int kChainMaxLayers = 40;
+constexpr int kChainMaxLayers = 32;     // the chain kernel keeps its layer table in shared memory (48 bytes per layer)
 
 // m-blocks per slab of the fine-net chain kernel (default kChainSlabMb = 56: three rounds of the 74 pairs per layer,
 // 3 x 29 MB of activations); MOFA_B200_CHAIN_SLAB overrides it for measurements
@@ -499,21 +529,57 @@ int run_chain(mofa_b200_ctx* c, Net& net, const Workspace& ws, int64_t P_rows, c
     };
     const int pair_groups = 2;
     int tiles_per_mb = 0, nt = 0, nt_last = 0;
+    // FP8 variant: which dense steps take e4m3 operands (the first fp8_layers plain layers), and which therefore must
+    // PRODUCE e4m3 (every consumer of a tensor has the same operand type by construction of the network)
+    std::vector<int> f8_in, f8_out;
+    {
+      std::vector<const Step*> dn;
+      for (const Step& st : net.program)
+        if (st.kind == 0) dn.push_back(&st);
+      f8_in.assign(dn.size(), 0);
+      f8_out.assign(dn.size(), 0);
+      int plain = 0;
+      for (size_t i = 0; i < dn.size(); ++i)
+        if (net.layers[dn[i]->layer].w8 != nullptr && plain++ < c->fp8_layers) f8_in[i] = 1;
+      for (size_t i = 0; i < dn.size(); ++i) {
+        int n8 = 0, n16 = 0;
+        for (size_t j = 0; j < dn.size(); ++j)
+          for (int k = 0; k < net.layers[dn[j]->layer].nseg; ++k)
+            if (dn[j]->in_step[k] == dn[i]->ord) (f8_in[j] ? n8 : n16)++;
+        if (n8 > 0 && n16 > 0) return fail("chain kernel (FP8): a tensor has consumers of both operand types");
+        f8_out[i] = n8 > 0 ? 1 : 0;
+      }
+    }
+    int dense_i = -1;
     for (const Step& st : net.program) {
       if (st.kind != 0) continue;
+      ++dense_i;
       const Layer& L = net.layers[st.layer];
       ChainLayerDesc d;
       memset(&d, 0, sizeof(d));
-      d.kb0 = L.K[0] / 64;
+      d.fp8_in = f8_in[dense_i];
+      d.fp8_out = f8_out[dense_i];
+      d.colscale = d.fp8_in ? L.colscale8 : nullptr;
+      d.kb0 = L.K[0] / (d.fp8_in ? 128 : 64);
       d.kb1 = L.nseg > 1 ? L.K[1] / 64 : 0;
       d.n_tiles = L.N / 256;
       d.N = L.N;
       d.bias = L.bias_eff;
       d.relu = 1;
       d.store_c = 1;
-      if ((d.mapA0 = src_map(st.in[0], L.K[0], &d.a0_global)) < 0) return 1;
-      maps.push_back(L.tmB2[0]);
-      d.mapB0 = static_cast<int>(maps.size()) - 1;
+      if (d.fp8_in) {        // e4m3 view of the same activation buffer: [slab_rows, K] bytes
+        CUtensorMap m;
+        if (make_tmap_u8(c, &m, ws.T[st.in[0] - SRC_T0], (uint64_t)slab_rows, (uint64_t)L.K[0], (uint64_t)L.K[0], 128, 128)) return 1;
+        maps.push_back(m);
+        d.mapA0 = static_cast<int>(maps.size()) - 1;
+        d.a0_global = 0;
+        maps.push_back(L.tmB8);
+        d.mapB0 = static_cast<int>(maps.size()) - 1;
+      } else {
+        if ((d.mapA0 = src_map(st.in[0], L.K[0], &d.a0_global)) < 0) return 1;
+        maps.push_back(L.tmB2[0]);
+        d.mapB0 = static_cast<int>(maps.size()) - 1;
+      }
       d.mapA1 = d.mapA0;
       d.mapB1 = d.mapB0;
       if (L.nseg > 1) {
@@ -530,7 +596,9 @@ int run_chain(mofa_b200_ctx* c, Net& net, const Workspace& ws, int64_t P_rows, c
       {
         CUtensorMap m;
         // output map: 32-column boxes (the epilogue stages and stores half a 64-column block at a time, double-buffered)
-        if (make_tmap_2d(c, &m, ws.T[st.out - SRC_T0], (uint64_t)slab_rows, (uint64_t)L.N, (uint64_t)L.N, 128, 32)) return 1;
+        if (d.fp8_out) {
+          if (make_tmap_u8(c, &m, ws.T[st.out - SRC_T0], (uint64_t)slab_rows, (uint64_t)L.N, (uint64_t)L.N, 128, 32)) return 1;
+        } else if (make_tmap_2d(c, &m, ws.T[st.out - SRC_T0], (uint64_t)slab_rows, (uint64_t)L.N, (uint64_t)L.N, 128, 32)) return 1;
         maps.push_back(m);
         d.mapC = static_cast<int>(maps.size()) - 1;
       }
@@ -815,6 +883,11 @@ int mofa_b200_create(mofa_b200_ctx** out, int device) {
     v = getenv("MOFA_B200_FINE_PER_LAYER");
     c->chain_fine = !(v && v[0] == '1');
     if (e == cudaSuccess) e = mofa::fine_chain_configure();
+    v = getenv("MOFA_B200_FP8");
+    if (v && v[0] != '\0' && v[0] != '0') {
+      const int n = atoi(v);
+      c->fp8_layers = n == 1 ? 1000 : n;
+    }
     v = getenv("MOFA_B200_COARSE_FP16");
     c->split_coarse = !(v && v[0] == '1');
     if (e == cudaSuccess) e = mofa::coarse_fused_configure();
@@ -905,6 +978,10 @@ int mofa_b200_load_weights(mofa_b200_ctx* c, int net_id, int W, int D, const flo
           CK(launch_pack_weight_lo(w, L.in_total, L.seg_c0[i], L.seg_kreal[i], L.K[i], L.N, L.wlo[i], s));
           c->launches++;
         }
+      }
+      if (L.w8) {
+        CK(launch_pack_weight_fp8(w, L.in_total, L.seg_c0[0], L.seg_kreal[0], L.N, 8.0f, L.w8, L.colscale8, s));
+        c->launches++;
       }
       CK(cudaMemcpyAsync(L.bias_raw, b, sizeof(float) * L.N, cudaMemcpyDeviceToDevice, s));
       if (L.fold_n > 0)

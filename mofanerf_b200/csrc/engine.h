@@ -142,6 +142,10 @@ size_t coarse_split_park_bytes(int num_sms);
 cudaError_t launch_view_vec(const float* dirs, int stride, int64_t n, const float* Wv, int n_out, float* out,
                             cudaStream_t s);
 // dst = fp16(w - float(fp16(w))): the low image of the split-precision weights (same layout as launch_pack_weight)
+// e4m3 image of a plain [nrows, k] layer with one scale per output row: dst8 = e4m3(w / s_n), s_n = max|w_n| / 448;
+// colscale[n] = s_n / act_scale (what the accumulator of an fp8 x fp8 product is multiplied by)
+cudaError_t launch_pack_weight_fp8(const float* src, int ld, int c0, int k, int nrows, float act_scale, uint8_t* dst8,
+                                   float* colscale, cudaStream_t s);
 cudaError_t launch_pack_weight_lo(const float* src, int ld, int c0, int k, int kpad, int nrows, __half* dst,
                                   cudaStream_t s);
 
@@ -156,6 +160,9 @@ struct ChainLayerDesc {
   int N;
   const float* bias;
   const float* head_w;
+  // opt-in FP8 variant (MOFA_B200_FP8): e4m3 operands for this layer (K blocks of 128 elements), e4m3 output for the next
+  int fp8_in, fp8_out;
+  const float* colscale;                  // [N] weight scale / activation scale, applied to the accumulator (fp8_in)
 };
 struct ChainParams {
   const CUtensorMap* maps;                // device array

@@ -45,8 +45,8 @@ struct ChainSmem {
   static constexpr int OFF_BAR = OFF_C + 2 * C_BYTES;            // one staging buffer per epilogue group
   static constexpr int N_BARS = 2 * kChainStages + 4;
   static constexpr int OFF_TPTR = OFF_BAR + N_BARS * 8;
-  static constexpr int OFF_LAYERS = OFF_TPTR + 16;              // compact per-layer table (40 bytes x kChainMaxLayersSm)
-  static constexpr int TOTAL = OFF_LAYERS + 40 * 40;
+  static constexpr int OFF_LAYERS = OFF_TPTR + 16;              // compact per-layer table (48 bytes x 32 layers)
+  static constexpr int TOTAL = OFF_LAYERS + 48 * 32;
   static constexpr int DYN_BYTES = TOTAL + 1024;
 };
 static_assert(ChainSmem::DYN_BYTES <= 232448, "chain kernel exceeds the 227 KB shared-memory limit");
@@ -57,11 +57,12 @@ static_assert(ChainSmem::DYN_BYTES <= 232448, "chain kernel exceeds the 227 KB s
 struct ChainLayerSm {
   const float* bias;
   const float* head_w;
+  const float* colscale;
   uint16_t mapA0, mapA1, mapB0, mapB1, mapC, N;
   uint8_t kb0, kb1, a0_global, a1_global, relu, store_c, head_n, head_slot0;
-  uint8_t pad[4];
+  uint8_t fp8_in, fp8_out, pad[2];
 };
-static_assert(sizeof(ChainLayerSm) == 40, "ChainLayerSm layout");
+static_assert(sizeof(ChainLayerSm) == 48, "ChainLayerSm layout");
 
 struct ChainTile {
   int layer, mb_local, mb_global, n;
@@ -125,9 +126,13 @@ __device__ __forceinline__ void wait_counter(const uint32_t* ctr, uint32_t need)
 // In this kernel the SM's L1 is invalidated twice per tile (cp.async.bulk.wait_group before a tile is published), so
 // bias loads issued where they are used — fine in the per-layer kernels, where they hit L1 — each exposed an L2 round
 // trip: the epilogue became the critical path (tensor pipe 63 % active, ncu).
-template <int HEAD>
-__device__ __forceinline__ void chain_epilogue(const EpiParams& p, const void* tmC, uint32_t acc_addr, const EpiGroup& g,
-                                               int m0, int n0, int row, long long hrow0) {
+// F8IN: the accumulator is an e4m3 x e4m3 product and is multiplied by colscale[col] before the bias.  F8OUT: the
+// activation is written as e4m3 (x kFp8ActScale, saturating) in 32-byte rows instead of fp16 in 64-byte rows.
+constexpr float kFp8ActScale = 8.0f;
+template <int HEAD, bool F8IN, bool F8OUT>
+__device__ __forceinline__ void chain_epilogue(const EpiParams& p, const float* __restrict__ colscale, const void* tmC,
+                                               uint32_t acc_addr, const EpiGroup& g, int m0, int n0, int row,
+                                               long long hrow0) {
   float hacc[3] = {0.f, 0.f, 0.f};
   const int col_base = n0 + g.cb0 * 64;
   float4 bcur[8], bnext[8];
@@ -146,6 +151,12 @@ __device__ __forceinline__ void chain_epilogue(const EpiParams& p, const void* t
     const uint32_t cbuf = g.cbuf0 + (q & 1) * (128 * 32 * 2);
     uint32_t v[32];
     tmem_ld_32x32b_x32(acc_addr + cb * 64 + h * 32, v);
+    float4 cs[F8IN ? 8 : 1];
+    if constexpr (F8IN) {
+      const float4* c4 = reinterpret_cast<const float4*>(colscale + ncol);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) cs[i] = ldg_f4_pinned(c4 + i);
+    }
     constexpr int HB = (HEAD == 3) ? 1 : 4;           // 8-column blocks of head weights per fetch
     constexpr int NHW = HEAD > 0 ? HEAD * 2 * HB : 1;
     float4 hw[2][NHW];
@@ -176,7 +187,14 @@ __device__ __forceinline__ void chain_epilogue(const EpiParams& p, const void* t
       float f[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        float x = __uint_as_float(v[j * 8 + e]) + bb[e];
+        float x = __uint_as_float(v[j * 8 + e]);
+        if constexpr (F8IN) {
+          const float4 c0 = cs[2 * j], c1 = cs[2 * j + 1];
+          const float cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+          x = x * cc[e] + bb[e];
+        } else {
+          x += bb[e];
+        }
         if (p.relu) x = fmaxf(x, 0.0f);
         f[e] = fminf(fmaxf(x, -65504.0f), 65504.0f);
       }
@@ -199,7 +217,17 @@ __device__ __forceinline__ void chain_epilogue(const EpiParams& p, const void* t
                       f[6] * w1.z + f[7] * w1.w;
         }
       }
-      if (p.store_c) {
+      if constexpr (F8OUT) {
+        if (p.store_c) {      // 8 columns -> 8 bytes of this row's 32-byte staging row (no swizzle)
+          uint16_t pk[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(pk[e]) : "f"(f[2 * e + 1] * kFp8ActScale), "f"(f[2 * e] * kFp8ActScale));
+          const uint32_t w0 = static_cast<uint32_t>(pk[0]) | (static_cast<uint32_t>(pk[1]) << 16);
+          const uint32_t w1 = static_cast<uint32_t>(pk[2]) | (static_cast<uint32_t>(pk[3]) << 16);
+          asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(cbuf + row * 32 + j * 8), "r"(w0), "r"(w1) : "memory");
+        }
+      } else if (p.store_c) {
         __half2 h0 = __floats2half2_rn(f[0], f[1]);
         __half2 h1 = __floats2half2_rn(f[2], f[3]);
         __half2 h2 = __floats2half2_rn(f[4], f[5]);
@@ -277,7 +305,9 @@ fine_chain_kernel(const ChainParams p) {
       q.mapA0 = d.mapA0; q.mapA1 = d.mapA1; q.mapB0 = d.mapB0; q.mapB1 = d.mapB1; q.mapC = d.mapC; q.N = d.N;
       q.kb0 = d.kb0; q.kb1 = d.kb1; q.a0_global = d.a0_global; q.a1_global = d.a1_global; q.relu = d.relu;
       q.store_c = d.store_c; q.head_n = d.head_n; q.head_slot0 = d.head_slot0;
-      q.pad[0] = q.pad[1] = q.pad[2] = q.pad[3] = 0;
+      q.colscale = d.colscale;
+      q.fp8_in = d.fp8_in; q.fp8_out = d.fp8_out;
+      q.pad[0] = q.pad[1] = 0;
       lt[i] = q;
     }
   }
@@ -324,6 +354,7 @@ fine_chain_kernel(const ChainParams p) {
         const int m_a1 = d.a1_global ? mg : ml;
         const int n0 = c.n * BN + static_cast<int>(rank) * 128;
         const int total_kb = d.kb0 + d.kb1;
+        const int kstep = d.fp8_in ? 128 : 64;       // elements per 128-byte K block (e4m3 / fp16)
         for (int kb = 0; kb < total_kb; ++kb) {
           mbar_wait(empty0 + 8 * stage, phase ^ 1u);
           const uint32_t fb_local = full0 + 8 * stage;
@@ -333,10 +364,10 @@ fine_chain_kernel(const ChainParams p) {
           if (elect_one()) {
             if (leader) mbar_expect_tx(fb_local, 2 * L::STAGE_BYTES);
             if (kb < d.kb0) {
-              tma_load_2d_cg2(sa, p.maps + d.mapA0, fb, kb * 64, m_a0);
-              tma_load_2d_cg2(sb, p.maps + d.mapB0, fb, kb * 64, n0);
+              tma_load_2d_cg2(sa, p.maps + d.mapA0, fb, kb * kstep, m_a0);
+              tma_load_2d_cg2(sb, p.maps + d.mapB0, fb, kb * kstep, n0);
             } else {
-              const int k = (kb - d.kb0) * 64;
+              const int k = (kb - d.kb0) * kstep;
               tma_load_2d_cg2(sa, p.maps + d.mapA1, fb, k, m_a1);
               tma_load_2d_cg2(sb, p.maps + d.mapB1, fb, k, n0);
             }
@@ -357,6 +388,7 @@ fine_chain_kernel(const ChainParams p) {
       for (long long t = pair; t < num_items; t += num_pairs, ++it) {
         const ChainTile c = chain_decode(p, t);
         const int total_kb = lsm[c.layer].kb0 + lsm[c.layer].kb1;
+        const bool f8 = lsm[c.layer].fp8_in != 0;
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
         mbar_wait(tempty0 + 8 * as, aphase ^ 1u);
@@ -369,8 +401,13 @@ fine_chain_kernel(const ChainParams p) {
           const uint64_t da = umma_desc_sw128_kmajor(sa);
           const uint64_t db = umma_desc_sw128_kmajor(sa + L::A_BYTES);
           if (elect_one()) {
+            if (f8) {      // same descriptors and K stepping (32 bytes per instruction): only the operand kind differs
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_f16_ss_cg2(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < 4; ++k) umma_f8_ss_cg2(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            } else {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_f16_ss_cg2(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
             umma_commit_cg2_mc(empty0 + 8 * stage, 0x3);
             if (kb == total_kb - 1) umma_commit_cg2_mc(tfull0 + 8 * as, 0x3);
           }
@@ -423,9 +460,19 @@ fine_chain_kernel(const ChainParams p) {
       tc_fence_after();
       {
         const uint32_t acc_addr = tmem_base + lane_base + as * BN;
-        if (d.head_n == 0) chain_epilogue<0>(e, p.maps + d.mapC, acc_addr, g, ml, c.n * BN, row, mg);
-        else if (d.head_n == 1) chain_epilogue<1>(e, p.maps + d.mapC, acc_addr, g, ml, c.n * BN, row, mg);
-        else chain_epilogue<3>(e, p.maps + d.mapC, acc_addr, g, ml, c.n * BN, row, mg);
+        const void* mc = p.maps + d.mapC;
+        const int nn = c.n * BN;
+        if (d.head_n == 0) {
+          if (!d.fp8_in && !d.fp8_out) chain_epilogue<0, false, false>(e, d.colscale, mc, acc_addr, g, ml, nn, row, mg);
+          else if (d.fp8_in && d.fp8_out) chain_epilogue<0, true, true>(e, d.colscale, mc, acc_addr, g, ml, nn, row, mg);
+          else if (d.fp8_in) chain_epilogue<0, true, false>(e, d.colscale, mc, acc_addr, g, ml, nn, row, mg);
+          else chain_epilogue<0, false, true>(e, d.colscale, mc, acc_addr, g, ml, nn, row, mg);
+        } else if (d.head_n == 1) {
+          if (d.fp8_in) chain_epilogue<1, true, false>(e, d.colscale, mc, acc_addr, g, ml, nn, row, mg);
+          else chain_epilogue<1, false, false>(e, d.colscale, mc, acc_addr, g, ml, nn, row, mg);
+        } else {
+          chain_epilogue<3, false, false>(e, d.colscale, mc, acc_addr, g, ml, nn, row, mg);
+        }
       }
       tc_fence_before();
       __syncwarp();

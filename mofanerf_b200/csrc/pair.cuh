@@ -59,6 +59,17 @@ __device__ __forceinline__ void umma_f16_ss_cg2(uint32_t tmem_d, uint64_t desc_a
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// kind::f8f6f4: 8-bit operands (e4m3 here: format code 0 in the instruction descriptor, the same bit pattern as fp16 for
+// kind::f16), K = 32 per instruction, fp32 accumulate — twice the tensor rate of kind::f16
+__device__ __forceinline__ void umma_f8_ss_cg2(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // arrives on the barrier at the same shared-memory offset in every CTA of `mask`
 __device__ __forceinline__ void umma_commit_cg2_mc(uint32_t bar, uint16_t mask) {
   asm volatile(

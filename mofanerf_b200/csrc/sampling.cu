@@ -604,6 +604,34 @@ cudaError_t launch_pack_weight(const float* src, int ld, int c0, int k, int kpad
   return cudaGetLastError();
 }
 
+// one warp per output row: row maximum -> scale -> e4m3 (round to nearest even, saturating)
+__global__ void pack_weight_fp8_kernel(const float* __restrict__ src, int ld, int c0, int k, int nrows, float act_scale,
+                                       uint8_t* __restrict__ dst8, float* __restrict__ colscale) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= nrows) return;
+  const float* w = src + static_cast<int64_t>(row) * ld + c0;
+  float m = 0.f;
+  for (int j = lane; j < k; j += 32) m = fmaxf(m, fabsf(w[j]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  const float sc = fmaxf(m, 1e-12f) / 448.0f;
+  if (lane == 0) colscale[row] = sc / act_scale;
+  for (int j = lane * 2; j < k; j += 64) {
+    const float a = w[j] / sc, b = (j + 1 < k) ? w[j + 1] / sc : 0.f;
+    uint16_t pk;
+    asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(pk) : "f"(b), "f"(a));     // first operand -> upper byte
+    *reinterpret_cast<uint16_t*>(dst8 + static_cast<int64_t>(row) * k + j) = pk;
+  }
+}
+
+cudaError_t launch_pack_weight_fp8(const float* src, int ld, int c0, int k, int nrows, float act_scale, uint8_t* dst8,
+                                   float* colscale, cudaStream_t s) {
+  if ((k & 1) != 0) return cudaErrorInvalidValue;
+  pack_weight_fp8_kernel<<<(nrows + 7) / 8, 256, 0, s>>>(src, ld, c0, k, nrows, act_scale, dst8, colscale);
+  return cudaGetLastError();
+}
+
 __global__ void pack_weight_lo_kernel(const float* __restrict__ src, int ld, int c0, int k, int kpad, int nrows,
                                       __half* __restrict__ dst) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;

@@ -203,3 +203,48 @@ def test_fine_chain_kernel_on_a_512_wide_net():
     assert torch.equal(outs["chain"]["raw"][..., 3], outs["per_layer"]["raw"][..., 3])          # sigma: same tiles, same order
     assert (outs["chain"]["raw"] - outs["per_layer"]["raw"]).abs().max().item() <= 1e-4
     assert (outs["chain"]["rgb_map"] - outs["per_layer"]["rgb_map"]).abs().max().item() <= 1e-5
+
+
+def test_fp8_variant_matches_its_emulation_and_is_not_the_default():
+    """MOFA_B200_FP8 (opt-in measurement mode): the 19 plain 1024 -> 1024 fine layers run as
+    tcgen05.mma.kind::f8f6f4 with e4m3 operands.  It must (a) compute what the emulation in tools/fp8_parity_study.py
+    says such a variant computes (per-channel weight scales, activations x8, saturating round-to-nearest) and (b) stay
+    OFF by default: the default engine on the same rays is the fp16 result of the fixtures."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import fp8_parity_study as F8
+    from mofanerf_b200.engine import Engine
+    meta, inp, gold = load_case("cfg4_800_exp9")
+    c, f, s = build_case_nets(meta)
+    n = 64
+    rays = O.make_ray_batch(inp["rays_o"][:n], inp["rays_d"][:n], 8.0, 26.0)
+    em = O.expression_mod(s, inp["shape"], inp["exp"])
+    with torch.no_grad():
+        emu = O.render_rays(rays, c, f, inp["shape"], em, inp["tex"], forward_fn=F8.make_forward(19), retraw=True)
+    res = {}
+    for mode in ("fp8", "default"):
+        if mode == "fp8":
+            os.environ["MOFA_B200_FP8"] = "1"
+        try:
+            eng = Engine(DEV)
+        finally:
+            os.environ.pop("MOFA_B200_FP8", None)
+        eng.load_network(0, c.to(DEV))
+        eng.load_network(1, f.to(DEV))
+        eng.set_latents(inp["shape"], em, inp["tex"])
+        pad = torch.cat([rays, torch.zeros(n, 1)], 1).to(DEV)
+        res[mode] = {k: v.cpu() for k, v in eng.render_rays(pad, 64, 64, retraw=True).items()}
+        torch.cuda.synchronize()
+        eng.close()
+    c.cpu(); f.cpu()
+    d_emu = (res["fp8"]["rgb_map"] - emu["rgb_map"]).abs()
+    ps_emu = O.psnr(res["fp8"]["rgb_map"], emu["rgb_map"])
+    ps_ref = O.psnr(res["fp8"]["rgb_map"], gold["rgb_map"][:n])
+    ps_def = O.psnr(res["default"]["rgb_map"], gold["rgb_map"][:n])
+    parity_log.record("fp8 variant (19 layers, opt-in)", vs_emulation_max=d_emu.max().item(), vs_emulation_psnr_db=ps_emu,
+                      vs_reference_psnr_db=ps_ref, default_vs_reference_psnr_db=ps_def)
+    print(f"[parity] fp8 engine vs emulation: max {d_emu.max().item():.2e} psnr {ps_emu:.1f} dB; vs reference {ps_ref:.1f} dB "
+          f"(default engine {ps_def:.1f} dB)")
+    assert ps_emu >= 45.0, f"the FP8 kernels do not compute the emulated FP8 arithmetic: {ps_emu:.1f} dB"
+    assert 25.0 <= ps_ref <= 50.0          # a different product: well below the default path
+    assert ps_def >= 60.0
