@@ -750,6 +750,11 @@ def main():
                                       "share_of_step": prof[0]["ms"] / (ms_dev * args.steps)},
                      "whole_step_tflops": flop_step / (ms_dev / 1e3) / 1e12},
     }
+    if os.environ.get("MOFA_B200_FP8", "0") not in ("", "0"):     # opt-in measurement mode: label it, it is NOT the headline
+        line["dtype"] = ("OPT-IN FP8 VARIANT (MOFA_B200_FP8): e4m3 operands / f32 accumulate in the plain 1024->1024 fine layers, "
+                         "f16 elsewhere in the fine net; PSNR vs reference 35.7 dB (tests/test_gpu_round2.py, "
+                         "profiles/r02_fp8_parity_study.json) - outside the stated tolerance, not a drop-in")
+        line["metric"] += " [FP8 variant]"
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args.n_samples, args.n_importance, args.cpu_sample_rays)
     if mg_check is not None:
