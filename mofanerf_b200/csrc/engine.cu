@@ -124,8 +124,8 @@ struct mofa_b200_ctx {
   bool latents_set = false;
   bool pair_kernel = true;       // cta_group::2 kernel for N % 256 == 0 (MOFA_B200_DENSE_1CTA=1 disables)
   bool fused_coarse = true;      // one persistent kernel for a W == 256 net (MOFA_B200_NO_FUSED_COARSE=1 disables)
-  int fp8_layers = 0;            // MOFA_B200_FP8=n: the first n plain W -> W layers of a wide net run with e4m3 operands
-                                 // (1 = all of them).  NOT the default: fails the stated tolerance (profiles/r02_fp8_parity_study.json)
+  int fp8_layers = 0;            // MOFA_B200_FP8=1|all: every plain W -> W layer of a wide net runs with e4m3 operands;
+                                 // MOFA_B200_FP8=layers=K: the first K of them.  NOT the default: fails the stated tolerance (profiles/r02_fp8_parity_study.json)
   bool importing = false;        // load_weights is being driven by mofa_b200_import_packed: build the structure, read no sources
   bool chain_fine = true;        // all dense layers of a W >= 512 net in one persistent launch, activations L2-resident
                                  // (fine_chain.cu); MOFA_B200_FINE_PER_LAYER=1 selects one launch per layer (round 1)
@@ -884,10 +884,8 @@ int mofa_b200_create(mofa_b200_ctx** out, int device) {
     c->chain_fine = !(v && v[0] == '1');
     if (e == cudaSuccess) e = mofa::fine_chain_configure();
     v = getenv("MOFA_B200_FP8");
-    if (v && v[0] != '\0' && v[0] != '0') {
-      const int n = atoi(v);
-      c->fp8_layers = n == 1 ? 1000 : n;
-    }
+    if (v && strncmp(v, "layers=", 7) == 0) c->fp8_layers = atoi(v + 7);         // the first K plain layers (parity sweep)
+    else if (v && (strcmp(v, "1") == 0 || strcmp(v, "all") == 0)) c->fp8_layers = 1000;   // all of them
     v = getenv("MOFA_B200_COARSE_FP16");
     c->split_coarse = !(v && v[0] == '1');
     if (e == cudaSuccess) e = mofa::coarse_fused_configure();
