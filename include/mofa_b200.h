@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define MOFA_B200_ABI_VERSION 1
+#define MOFA_B200_ABI_VERSION 2   /* 2: bwd_args.loss_scale_dev, generate_rays, packed-weight blob */
 
 typedef struct mofa_b200_ctx mofa_b200_ctx;
 

@@ -109,7 +109,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)   # AttributeError if the library does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if lib.mofa_b200_abi_version() != 1:
+    if lib.mofa_b200_abi_version() != 2:
         raise RuntimeError("libmofa_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -449,13 +449,15 @@ class B200Renderer(torch.nn.Module):
             print(i, time.time() - t)
             t = time.time()
             tex, ev = ahead
+            # frame i + 1's texture code is enqueued on the side stream BEFORE frame i's kernels go to the main stream: it
+            # only waits for what the main stream held up to here, so it runs next to (in the gaps of) frame i's rendering
+            if i + 1 < n:
+                ahead = encode_ahead(i + 1)
             if ev is not None:
                 torch.cuda.current_stream().wait_event(ev)
             rgb, disp, acc, _ = self.render(H, W, K, chunk=chunk, c2w=c2w[:3, :4],
                                             shapeCodes=shapeCodes[i, :].reshape(1, -1), uvMap=uvMap[i, :],
                                             expType=expType[i], _tex=tex, **render_kwargs)
-            if i + 1 < n:
-                ahead = encode_ahead(i + 1)
             fn = None
             if savedir is not None:
                 fn = os.path.join(savedir, '{}.png'.format(name) if name is not None else '{:03d}.png'.format(i))

@@ -27,7 +27,7 @@ def test_library_builds_and_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in include/mofa_b200.h but not exported"
         assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
     assert set(_lib.SIGNATURES) == set(declared)
-    assert _lib.load().mofa_b200_abi_version() == 1
+    assert _lib.load().mofa_b200_abi_version() == 2
 
 
 def test_render_args_struct_matches_header_layout():
