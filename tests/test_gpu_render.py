@@ -161,6 +161,35 @@ def test_frame_crop_config5_identities_through_render(name):
     check_maps(name, _maps(*out), gold)
 
 
+def test_psnr_to_target_within_0p1_db_of_the_reference():
+    """north_star: "rendered PSNR within 0.1 dB of reference on the fit/render demo".  Without a trained checkpoint the
+    demo is emulated with the reference's own outputs: the image rendered with expression slot 9 is the TARGET, the
+    renders with slots 14 and 2 (and of other identities) play the fitted result.  PSNR(engine render, target) must equal
+    PSNR(reference render, target) to 0.1 dB — the reference renders are the fixtures produced by the unmodified
+    reference."""
+    meta, inp9, gold9 = load_case("cfg4_800_exp9")
+    target = gold9["rgb_map"]
+    c, f, s, r = build_reference_like(int(meta["seed"]))
+    r = r.to(DEV)
+    for name in ("cfg4_800_exp14", "cfg4_800_exp2"):
+        m2, inp, gold = load_case(name)
+        e = int(inp["exp_slot"])
+        # same camera and ray subset as the target?  the crops use different random ray subsets: render the TARGET's rays
+        with torch.no_grad():
+            out = r.render_fitting(int(meta["H"]), int(meta["W"]), inp9["K"].numpy(), chunk=1 << 20,
+                                   rays=(inp9["rays_o"].to(DEV), inp9["rays_d"].to(DEV)), shapeCodes=inp["shape"].to(DEV),
+                                   uvCodes=inp["tex"].to(DEV), expType=20, expCodes=r.expCodes_Sigma[e],
+                                   **_crop_kwargs(meta, c, f))[0].float().cpu()
+            rays = O.make_ray_batch(inp9["rays_o"], inp9["rays_d"], 8.0, 26.0)
+            ref = O.render_rays(rays[:64], c.cpu(), f.cpu(), inp["shape"], O.expression_mod(s, inp["shape"], inp["exp"]),
+                                inp["tex"])["rgb_map"]
+        p_eng = O.psnr(out[:64], target[:64])
+        p_ref = O.psnr(ref, target[:64])
+        parity_log.record(f"psnr-to-target[{name} vs exp9 target]", engine_db=p_eng, reference_db=p_ref, delta_db=abs(p_eng - p_ref))
+        print(f"[parity] PSNR to target: engine {p_eng:.3f} dB, reference {p_ref:.3f} dB")
+        assert abs(p_eng - p_ref) <= 0.1, f"{name}: engine {p_eng:.3f} dB vs reference {p_ref:.3f} dB"
+
+
 def test_simt_and_tensor_core_paths_agree():
     meta, inp, gold = load_case("small_w256")
     nets = build_case_nets(meta)
