@@ -17,6 +17,12 @@ with fp32 accumulation, every other stage is fp32.  For rendered maps in [0,1]:
     reference shows the same sensitivity between its own CPU and CUDA runs).  The SIMT verification kernel (single fp16
     operands, different accumulation order) is held to the same end-to-end bounds and agrees with the default path to
     2e-3 on the coarse maps (its own fp16 error).
+  * on a LARGE sample of the bench frame (test_frame_sample_error_distribution_with_the_references_own_yardsticks, 4096
+    rays) the bound is a distribution, not one maximum: the reference's own last-interval step (relu(sigma) * 1e10,
+    models/render_class.py:449) flips the opacity of ~3 in 8192 rays of the synthetic frame for ANY finite-precision
+    arithmetic — the reference's default TF32 mode flips the same rays — so the test asserts p50 / p99 / the fraction of
+    rays within 3e-2, that every flip sits on |sigma_last| < 2e-2 in the reference, and that the engine is closer to the
+    fp32 reference than the reference run with TF32 matmuls is (measured 3x closer).
 Ray order is bit-exact by construction and tested (output row i <-> input ray i).
 """
 import numpy as np
@@ -353,3 +359,60 @@ def test_training_mode_forward_equals_inference_forward():
     assert b[0].requires_grad and b[0].grad_fn is not None
     assert (a[3]["rgb0"] - b[3]["rgb0"].detach()).abs().max().item() <= 2e-3
     assert (a[0] - b[0].detach()).abs().max().item() <= 2e-2 and (a[2] - b[2].detach()).abs().max().item() <= 2e-2
+
+
+def test_frame_sample_error_distribution_with_the_references_own_yardsticks():
+    """4096 rays spread over the whole 800x800 bench frame at the real widths (the fixtures above are 192-ray crops): the
+    DISTRIBUTION of the engine's per-ray error against the fp32 reference algorithm, next to the reference algorithm's
+    own deviation when its matmuls run in TF32 — the default of torch 1.9 (the reference's pinned version) on Ampere and
+    later GPUs, and the same 10-bit operand mantissa as the engine's fp16 fine net.
+
+    Why a distribution and not one maximum: raw2outputs gives the LAST sample of a ray an interval of 1e10
+    (models/render_class.py:449), so alpha_last = 1 - exp(-relu(sigma_last) * 1e10) is a step function of sigma_last.  A
+    ray whose last fine sample has |sigma| below the arithmetic's rounding (measured: fp16 chain p99 3e-3 on |sigma| ~ 0.5)
+    renders with acc = 1 or acc << 1 depending on a sign no finite-precision implementation reproduces ("opacity gate
+    flips": 3 of 8192 rays of this synthetic frame, for the engine AND for the TF32 reference, on the same rays).  The
+    random-init fine net makes this frame almost empty (median fine acc 0.03), which is the worst case for it."""
+    import bench
+    n = 4096
+    c, f, s = O.build_nets(0)
+    shape, tex, exp, ro, rd = bench.synth_inputs(800, 800)
+    idx = torch.linspace(0, ro.shape[0] - 1, n).long()
+    cg, fg, sg = c.to(DEV), f.to(DEV), s.to(DEV)
+    rays = O.make_ray_batch(ro[idx], rd[idx], 8.0, 26.0).to(DEV)
+    prev = torch.backends.cuda.matmul.allow_tf32
+    try:
+        with torch.no_grad(), torch.device(DEV):
+            em = O.expression_mod(sg, shape.to(DEV), exp.to(DEV))
+            torch.backends.cuda.matmul.allow_tf32 = False
+            ref = O.render_rays(rays, cg, fg, shape.to(DEV), em, tex.to(DEV), N_samples=64, N_importance=64,
+                                netchunk=196608, retraw=True)
+            torch.backends.cuda.matmul.allow_tf32 = True
+            tf = O.render_rays(rays, cg, fg, shape.to(DEV), em, tex.to(DEV), N_samples=64, N_importance=64, netchunk=196608)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    from mofanerf_b200 import B200Renderer
+    r = B200Renderer(expCodesLen=30).to(DEV)
+    r.idSpecificMod.load_state_dict(s.state_dict())
+    with torch.no_grad():
+        rgb, disp, acc, extras = r.render_fitting(
+            1, n, None, chunk=1 << 30, rays=(ro[idx].to(DEV), rd[idx].to(DEV)), shapeCodes=shape.to(DEV),
+            uvCodes=tex.to(DEV), expType=20, expCodes=exp.to(DEV), near=8.0, far=26.0, use_viewdirs=True, ndc=False,
+            network_fn=cg, network_fine=fg, N_samples=64, N_importance=64, perturb=0.0, raw_noise_std=0.0)
+    st = bench.parity_stats(rgb, acc, ref["rgb_map"], ref["acc_map"])
+    yt = bench.parity_stats(tf["rgb_map"], tf["acc_map"], ref["rgb_map"], ref["acc_map"])
+    for tag, d in (("engine_vs_fp32", st), ("reference_tf32_vs_fp32", yt)):
+        parity_log.record("frame_sample_4096_" + tag, rays=n, **{k: v for k, v in d.items()})
+    print(f"[parity] frame sample: engine {st}\n[parity] frame sample: TF32 reference {yt}")
+    # coarse maps stay fp32-class on the large sample too
+    assert (extras["rgb0"].reshape(-1, 3) - ref["rgb0"]).abs().max().item() <= 5e-5
+    # the distribution (measured on 8192 rays: p50 1.1e-4, p99 7.5e-3, 99.87 % of rays within 3e-2, 57 dB without the flips)
+    assert st["err_p50"] <= 3e-4 and st["err_p99"] <= 1.5e-2, st
+    assert st["frac_rays_within_3e-2"] >= 0.995, st
+    assert st["max_abs_rgb_excluding_gate_flips"] <= 8e-2 and st["psnr_db_excluding_gate_flips"] >= 50.0, st
+    # every opacity-gate flip is a ray whose REFERENCE sigma at the last sample is within rounding of zero
+    flips = (acc.reshape(-1) - ref["acc_map"].reshape(-1)).abs() > 0.5
+    sig_last = ref["raw"].reshape(n, -1, 4)[:, -1, 3]
+    assert flips.sum().item() <= 8 and bool((sig_last[flips].abs() < 2e-2).all()), sig_last[flips]
+    # the engine is at least as close to the fp32 reference as the reference's own TF32 mode (measured: 3x closer)
+    assert st["mean_abs_rgb"] <= yt["mean_abs_rgb"] and st["err_p99"] <= yt["err_p99"], (st, yt)
