@@ -229,10 +229,67 @@ def frame_crop_cases():
              renderer.expCodes_Sigma[e], exp_slot=e, uv_seed=300 + i, angle=angle)
 
 
+def frame_sample_case(n_rays=1024, bench_regime=False):
+    """Round-2 (late) fixture: a LARGE sample of the 800x800 frame at the real widths — every 625th ray — through the
+    unmodified reference's render_fitting (config #4 set-up, expression slot 9).  The 192-ray crops never met the
+    reference's own last-interval discontinuity (raw2outputs gives the last sample an interval of 1e10,
+    models/render_class.py:449: alpha_last is a step in sigma_last); a sample of this size does, so the fixture also
+    keeps the reference's pre-activation sigma of every ray's last fine sample (`sigma_last`) and the smallest
+    |sigma| along the ray."""
+    ref = ref_loader.load()
+    seed, W_c, D_c, W_f, D_f, H, W = (0 if bench_regime else 5), 256, 8, 1024, 10, 800, 800
+    coarse, fine, renderer = ref_loader.build_reference(seed, W_c, D_c, W_f, D_f)
+    oc, of, ostyle = O.build_nets(seed, W_c, D_c, W_f, D_f)
+    _check_same_nets(coarse, oc)
+    _check_same_nets(fine, of)
+    _check_same_nets(renderer.idSpecificMod, ostyle)
+    e = 9
+    if bench_regime:
+        # bench.py's synthetic frame (seed-0 nets, bench.synth_inputs latents and camera): the random-init fine net of
+        # this seed leaves the volume almost empty (median fine acc 0.03) — the regime in which the last-interval step
+        # and near-zero sigma decide single rays (DESIGN.md section 6)
+        import bench
+        shape, tex, exp_b, _, _ = bench.synth_inputs(H, W)
+        renderer.expCodes_Sigma[e] = exp_b
+        K, c2w = _camera(H, W, 30.0)
+    else:
+        shape, tex, _ = _latents(seed + 100)
+        K, c2w = _camera(H, W, 0.0)
+    ro, rd = ref.helpers.get_rays(H, W, K, c2w[:3, :4])
+    ro, rd = ro.reshape(-1, 3), rd.reshape(-1, 3)
+    idx = torch.linspace(0, H * W - 1, n_rays).long()
+    kwargs = dict(network_fn=coarse, network_fine=fine, N_samples=64, N_importance=64, perturb=0.0, raw_noise_std=0.0,
+                  white_bkgd=False, lindisp=False, use_viewdirs=True, ndc=False, near=8.0, far=26.0, retraw=True)
+    with torch.no_grad():
+        out = renderer.render_fitting(H, W, K, chunk=4096, rays=(ro[idx], rd[idx]), shapeCodes=shape, uvCodes=tex,
+                                      expType=20, expCodes=renderer.expCodes_Sigma[e], **kwargs)
+    res = dict(rgb_map=out[0], disp_map=out[1], acc_map=out[2])
+    for k in ("rgb0", "disp0", "acc0", "z_std"):
+        res[k] = out[3][k]
+    raw = out[3]["raw"].reshape(n_rays, -1, 4)
+    arrays = {f"out_{k}": v.detach().numpy().astype(np.float32) for k, v in res.items()}
+    arrays.update(sigma_last=raw[:, -1, 3].numpy().astype(np.float32),
+                  sigma_abs_min=raw[..., 3].abs().min(dim=1).values.numpy().astype(np.float32),
+                  rays_o=ro[idx].numpy(), rays_d=rd[idx].numpy(), ray_index=idx.numpy(), K=K, c2w=c2w.numpy(),
+                  shape=shape.numpy(), tex=tex.numpy(), exp=renderer.expCodes_Sigma[e].detach().numpy(), exp_slot=np.asarray(e))
+    meta = dict(seed=seed, W_c=W_c, D_c=D_c, W_f=W_f, D_f=D_f, H=H, W=W, N_samples=64, N_importance=64, perturb=0.0,
+                raw_noise_std=0.0, pytest=0, white_bkgd=0, lindisp=0, sigma_bias=np.nan, near=8.0, far=26.0)
+    for k, v in meta.items():
+        arrays[f"meta_{k}"] = np.asarray(v)
+    name = f"frame_sample_{'bench_' if bench_regime else ''}{n_rays}"
+    np.savez_compressed(os.path.join(OUT, f"{name}.npz"), **arrays)
+    print(f"[golden] {name}: rgb mean={arrays['out_rgb_map'].mean():.4f} acc median="
+          f"{np.median(arrays['out_acc_map']):.4f} min|sigma_last|={np.abs(arrays['sigma_last']).min():.2e}")
+
+
 def main():
     torch.set_num_threads(os.cpu_count())
     if "--r02" in sys.argv:      # only the round-2 frame crops (the round-1 fixtures are unchanged)
         frame_crop_cases()
+        return
+    if "--frame-sample" in sys.argv:
+        frame_sample_case()
+        frame_sample_case(bench_regime=True)
         return
     op_cases()
     # config #1 (plumbing): 64x64, 32 samples, coarse only

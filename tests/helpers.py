@@ -14,7 +14,7 @@ def load_case(name):
     meta = {k[5:]: z[k].item() for k in z.files if k.startswith("meta_")}
     out = {k[4:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("out_")}
     inp = {k: torch.from_numpy(z[k]) for k in ("rays_o", "rays_d", "shape", "tex", "exp")}
-    for k in ("ray_index", "K", "c2w", "exp_table", "exp_slot", "uv_seed", "angle"):   # round-2 frame crops
+    for k in ("ray_index", "K", "c2w", "exp_table", "exp_slot", "uv_seed", "angle", "sigma_last", "sigma_abs_min"):   # round-2 frame crops / samples
         if k in z.files:
             inp[k] = torch.from_numpy(z[k]) if z[k].ndim else z[k].item()
     return meta, inp, out
@@ -22,6 +22,9 @@ def load_case(name):
 
 FRAME_CROPS_CFG4 = ["cfg4_800_exp9", "cfg4_800_exp14", "cfg4_800_exp2"]
 FRAME_CROPS_CFG5 = ["cfg5_800_id0", "cfg5_800_id1", "cfg5_800_id2"]
+# 1024 rays spread over the 800x800 frame, unmodified reference: a dense field (the crops' nets) and bench.py's synthetic
+# frame (seed-0 nets: an almost empty fine field, where the reference's last-interval step decides single rays)
+FRAME_SAMPLES = ["frame_sample_1024", "frame_sample_bench_1024"]
 
 
 def build_reference_like(seed, W_c=256, D_c=8, W_f=1024, D_f=10):

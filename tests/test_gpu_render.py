@@ -31,7 +31,7 @@ import torch
 
 from oracle import mofa_oracle as O
 from tests import parity_log
-from tests.helpers import (FRAME_CROPS_CFG4, FRAME_CROPS_CFG5, build_case_nets, build_reference_like, case_randoms, load_case,
+from tests.helpers import (FRAME_CROPS_CFG4, FRAME_CROPS_CFG5, FRAME_SAMPLES, build_case_nets, build_reference_like, case_randoms, load_case,
                            oracle_render)
 
 pytestmark = pytest.mark.gpu
@@ -359,6 +359,47 @@ def test_training_mode_forward_equals_inference_forward():
     assert b[0].requires_grad and b[0].grad_fn is not None
     assert (a[3]["rgb0"] - b[3]["rgb0"].detach()).abs().max().item() <= 2e-3
     assert (a[0] - b[0].detach()).abs().max().item() <= 2e-2 and (a[2] - b[2].detach()).abs().max().item() <= 2e-2
+
+
+def _frame_sample_render(name):
+    meta, inp, gold = load_case(name)
+    c, f, s = build_case_nets(meta)
+    from mofanerf_b200 import B200Renderer
+    r = B200Renderer(expCodesLen=30).to(DEV)
+    r.idSpecificMod.load_state_dict(s.state_dict())
+    with torch.no_grad():
+        out = r.render_fitting(int(meta["H"]), int(meta["W"]), None, chunk=1 << 30,
+                               rays=(inp["rays_o"].to(DEV), inp["rays_d"].to(DEV)), shapeCodes=inp["shape"].to(DEV),
+                               uvCodes=inp["tex"].to(DEV), expType=20, expCodes=inp["exp"].to(DEV), **_crop_kwargs(meta, c, f))
+    return meta, inp, gold, _maps(*out)
+
+
+def test_frame_sample_1024_dense_field_against_the_reference():
+    """1024 rays spread over the 800x800 frame, rendered by the UNMODIFIED reference (tests/golden/frame_sample_1024.npz;
+    the nets of the config #4 / #5 crops: a dense field, acc ~ 1): the per-ray bound of the fixtures holds on the whole
+    sample."""
+    meta, inp, gold, got = _frame_sample_render("frame_sample_1024")
+    check_maps("frame_sample_1024", got, gold)
+
+
+def test_frame_sample_1024_bench_frame_against_the_reference():
+    """The same sample of bench.py's synthetic frame (seed-0 nets; tests/golden/frame_sample_bench_1024.npz, unmodified
+    reference on the CPU).  The random-init fine net of this seed leaves the volume almost empty (median fine acc 0.03)
+    and sigma hovers around 0 along whole rays: the reference's last-interval step (alpha_last = 1 - exp(-relu(sigma_last)
+    * 1e10), models/render_class.py:449) then decides single rays on the SIGN of a sigma that is below the rounding of
+    any 10-bit-mantissa arithmetic.  Asserted: the error distribution; that every opacity flip is such a ray according to
+    the reference's own stored sigma_last; the per-ray bound on all other rays."""
+    import bench
+    meta, inp, gold, got = _frame_sample_render("frame_sample_bench_1024")
+    st = bench.parity_stats(got["rgb_map"], got["acc_map"], gold["rgb_map"], gold["acc_map"])
+    parity_log.record("frame_sample_bench_1024", rays=gold["rgb_map"].shape[0], **st)
+    print(f"[parity] frame_sample_bench_1024: {st}")
+    assert (got["rgb0"] - gold["rgb0"]).abs().max().item() <= 5e-5            # the coarse pass is fp32-class here too
+    assert st["err_p50"] <= 3e-4 and st["err_p99"] <= 1.5e-2, st
+    assert st["frac_rays_within_3e-2"] >= 0.99, st
+    flips = (got["acc_map"].reshape(-1) - gold["acc_map"].reshape(-1)).abs() > 0.5
+    assert flips.sum().item() <= 4 and bool((inp["sigma_last"][flips].abs() < 2e-2).all()), inp["sigma_last"][flips]
+    assert st["max_abs_rgb_excluding_gate_flips"] <= 8e-2 and st["psnr_db_excluding_gate_flips"] >= 50.0, st
 
 
 def test_frame_sample_error_distribution_with_the_references_own_yardsticks():

@@ -8,7 +8,7 @@ import torch
 
 from oracle import mofa_oracle as O
 from oracle import ref_loader
-from tests.helpers import (FRAME_CROPS_CFG4, FRAME_CROPS_CFG5, GOLDEN, assert_close_nan, build_reference_like, load_case,
+from tests.helpers import (FRAME_CROPS_CFG4, FRAME_CROPS_CFG5, FRAME_SAMPLES, GOLDEN, assert_close_nan, build_reference_like, load_case,
                            oracle_render)
 
 OPS = np.load(f"{GOLDEN}/ops.npz")
@@ -94,6 +94,22 @@ def test_frame_crops(name):
     out, _, _ = oracle_render(meta, sub)
     for k, g in gold.items():
         assert_close_nan(out[k], g[:n], 1e-4, 1e-4, what=f"{name}:{k}")
+
+
+@pytest.mark.parametrize("name", FRAME_SAMPLES)
+def test_frame_samples(name):
+    """The 1024-ray frame samples (every 625th ray of the 800x800 frame through the unmodified reference): the oracle runs
+    48 of them spread over the sample; the stored sigma_last is the reference's pre-activation sigma of the last fine
+    sample, which the oracle's raw output must reproduce."""
+    meta, inp, gold = load_case(name)
+    sel = torch.linspace(0, inp["rays_o"].shape[0] - 1, 48).long()
+    sub = dict(inp, rays_o=inp["rays_o"][sel], rays_d=inp["rays_d"][sel])
+    ro, rd = O.get_rays(int(meta["H"]), int(meta["W"]), inp["K"].numpy(), inp["c2w"][:3, :4])
+    assert torch.equal(rd.reshape(-1, 3)[inp["ray_index"]], inp["rays_d"])
+    out, _, _ = oracle_render(meta, sub)
+    for k, g in gold.items():
+        assert_close_nan(out[k], g[sel], 1e-4, 1e-4, what=f"{name}:{k}")
+    assert_close_nan(out["raw"][:, -1, 3], inp["sigma_last"][sel], 2e-4, 1e-4, what=f"{name}:sigma_last")
 
 
 @pytest.mark.skipif(not ref_loader.available(), reason="reference tree not present on this box")
