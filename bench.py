@@ -215,7 +215,8 @@ def torch_gpu_baseline(n_s, n_i, dev, H=128, W=128, n_rays=8192, netchunk=196608
             torch.cuda.synchronize()
             out[f"rays_per_s_{name}"] = 3 * n_rays / (time.perf_counter() - t0)
             if keep is not None:
-                res = O.render_rays(rays, c, f, shape, em, tex, N_samples=n_s, N_importance=n_i, netchunk=netchunk)
+                res = O.render_rays(rays, c, f, shape, em, tex, N_samples=n_s, N_importance=n_i, netchunk=netchunk,
+                                    retraw=True)
                 if tf32:
                     keep.update(ref_tf32=res)
                 else:
@@ -224,17 +225,26 @@ def torch_gpu_baseline(n_s, n_i, dev, H=128, W=128, n_rays=8192, netchunk=196608
     return out
 
 
-def parity_stats(rgb, acc, ref_rgb, ref_acc):
-    """Per-ray comparison of two renderings of the same rays.  `opacity_gate_flips` counts rays whose accumulated opacity
-    differs by more than 0.5: raw2outputs gives the last sample an interval of 1e10 (models/render_class.py:449), so
+def parity_stats(rgb, acc, ref_rgb, ref_acc, sigma_last=None, ref_sigma_last=None):
+    """Per-ray comparison of two renderings of the same rays.  `opacity_gate_flips` counts rays on the reference's own
+    discontinuity: raw2outputs gives the last sample an interval of 1e10 (models/render_class.py:449), so
     alpha_last = 1 - exp(-relu(sigma_last) * 1e10) is a STEP in sigma_last — a ray whose last fine sample has sigma within
-    rounding of 0 renders with acc = 1 or acc << 1 depending on the sign; no finite-precision implementation (the reference
-    on another BLAS included) reproduces such a ray."""
+    rounding of 0 puts all of its remaining transmittance on that sample, or none of it, depending on a sign that no
+    finite-precision implementation (the reference on another BLAS included) reproduces.  With the pre-activation sigma
+    of the last sample of both renderings a flip is a ray where exactly one of them is positive; without, a ray whose
+    accumulated opacity differs by more than 0.5."""
     rgb, ref_rgb = rgb.reshape(-1, 3).double().cpu(), ref_rgb.reshape(-1, 3).double().cpu()
     acc, ref_acc = acc.reshape(-1).double().cpu(), ref_acc.reshape(-1).double().cpu()
     d = (rgb - ref_rgb).abs()
     err = d.max(dim=1).values
-    flips = (acc - ref_acc).abs() > 0.5
+    extra = {}
+    if sigma_last is not None and ref_sigma_last is not None:
+        sa, sr = sigma_last.reshape(-1).double().cpu(), ref_sigma_last.reshape(-1).double().cpu()
+        flips = (sa > 0) != (sr > 0)
+        extra["gate_flip_max_abs_sigma_last_of_reference"] = float(sr[flips].abs().max()) if flips.any() else 0.0
+        extra["gate_flips_with_visible_effect"] = int((flips & (err > 1e-2)).sum())
+    else:
+        flips = (acc - ref_acc).abs() > 0.5
     keep = ~flips
 
     def psnr(x):
@@ -242,13 +252,16 @@ def parity_stats(rgb, acc, ref_rgb, ref_acc):
         return 10.0 * float(np.log10(1.0 / m)) if m > 0 else float("inf")
 
     q = torch.quantile(err, torch.tensor([0.5, 0.99, 0.999], dtype=torch.float64))
-    return {"max_abs_rgb": float(err.max()), "mean_abs_rgb": float(d.mean()), "psnr_db": psnr(d),
-            "mean_rgb_of_reference": float(ref_rgb.mean()), "median_acc_of_reference": float(ref_acc.median()),
-            "err_p50": float(q[0]), "err_p99": float(q[1]), "err_p999": float(q[2]),
-            "rays_over_3e-2": int((err > 3e-2).sum()), "frac_rays_within_3e-2": float((err <= 3e-2).double().mean()),
-            "opacity_gate_flips": int(flips.sum()),
-            "max_abs_rgb_excluding_gate_flips": float(err[keep].max()) if keep.any() else 0.0,
-            "psnr_db_excluding_gate_flips": psnr(d[keep])}
+    out = {"max_abs_rgb": float(err.max()), "mean_abs_rgb": float(d.mean()), "psnr_db": psnr(d),
+           "mean_rgb_of_reference": float(ref_rgb.mean()), "median_acc_of_reference": float(ref_acc.median()),
+           "err_p50": float(q[0]), "err_p99": float(q[1]), "err_p999": float(q[2]),
+           "rays_over_3e-2": int((err > 3e-2).sum()), "frac_rays_within_3e-2": float((err <= 3e-2).double().mean()),
+           "opacity_gate_flips": int(flips.sum()),
+           "max_abs_rgb_excluding_gate_flips": float(err[keep].max()) if keep.any() else 0.0,
+           "rays_over_3e-2_excluding_gate_flips": int((err[keep] > 3e-2).sum()),
+           "psnr_db_excluding_gate_flips": psnr(d[keep])}
+    out.update(extra)
+    return out
 
 
 def parity_vs_oracle(renderer, keep, kw, dev):
@@ -266,18 +279,21 @@ def parity_vs_oracle(renderer, keep, kw, dev):
         with torch.no_grad():
             rgb, disp, acc, extras = renderer.render_fitting(
                 1, idx.numel(), None, chunk=1 << 30, rays=(ro[idx].to(dev), rd[idx].to(dev)), shapeCodes=shape.to(dev),
-                uvCodes=tex.to(dev), expType=20, expCodes=exp.to(dev), **dict(kw, network_fn=c, network_fine=f))
+                uvCodes=tex.to(dev), expType=20, expCodes=exp.to(dev), **dict(kw, network_fn=c, network_fine=f, retraw=True))
     finally:
         renderer.idSpecificMod.load_state_dict(style_state)
     ref = keep["ref"]
-    out = {"rays": int(idx.numel()),
-           "engine_vs_reference_fp32": parity_stats(rgb, acc, ref["rgb_map"], ref["acc_map"]),
+    n = int(idx.numel())
+    last = lambda raw: raw.reshape(n, -1, 4)[:, -1, 3]
+    out = {"rays": n,
+           "engine_vs_reference_fp32": parity_stats(rgb, acc, ref["rgb_map"], ref["acc_map"], last(extras["raw"]), last(ref["raw"])),
            "against": "oracle port of the reference algorithm, fp32 (TF32 off) PyTorch eager on the same GPU, same nets / latents / rays",
            "note": "synthetic random-init nets: along some rays the fine net's sigma hovers around 0, where relu(sigma) x (1e10 on "
                    "the last interval) makes the reference itself discontinuous; see parity_stats() and DESIGN.md section 6"}
     if "ref_tf32" in keep:
         out["reference_tf32_vs_reference_fp32"] = parity_stats(keep["ref_tf32"]["rgb_map"], keep["ref_tf32"]["acc_map"],
-                                                               ref["rgb_map"], ref["acc_map"])
+                                                               ref["rgb_map"], ref["acc_map"], last(keep["ref_tf32"]["raw"]),
+                                                               last(ref["raw"]))
     if "rgb0" in extras and "rgb0" in ref:
         out["max_abs_rgb0"] = float((extras["rgb0"].reshape(-1, 3) - ref["rgb0"].reshape(-1, 3)).abs().max().item())
     return out

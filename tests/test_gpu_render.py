@@ -370,7 +370,8 @@ def _frame_sample_render(name):
     with torch.no_grad():
         out = r.render_fitting(int(meta["H"]), int(meta["W"]), None, chunk=1 << 30,
                                rays=(inp["rays_o"].to(DEV), inp["rays_d"].to(DEV)), shapeCodes=inp["shape"].to(DEV),
-                               uvCodes=inp["tex"].to(DEV), expType=20, expCodes=inp["exp"].to(DEV), **_crop_kwargs(meta, c, f))
+                               uvCodes=inp["tex"].to(DEV), expType=20, expCodes=inp["exp"].to(DEV), retraw=True,
+                               **_crop_kwargs(meta, c, f))
     return meta, inp, gold, _maps(*out)
 
 
@@ -391,15 +392,18 @@ def test_frame_sample_1024_bench_frame_against_the_reference():
     the reference's own stored sigma_last; the per-ray bound on all other rays."""
     import bench
     meta, inp, gold, got = _frame_sample_render("frame_sample_bench_1024")
-    st = bench.parity_stats(got["rgb_map"], got["acc_map"], gold["rgb_map"], gold["acc_map"])
-    parity_log.record("frame_sample_bench_1024", rays=gold["rgb_map"].shape[0], **st)
+    n = gold["rgb_map"].shape[0]
+    sig_last = got["raw"].reshape(n, -1, 4)[:, -1, 3]
+    st = bench.parity_stats(got["rgb_map"], got["acc_map"], gold["rgb_map"], gold["acc_map"], sig_last, inp["sigma_last"])
+    parity_log.record("frame_sample_bench_1024", rays=n, **st)
     print(f"[parity] frame_sample_bench_1024: {st}")
     assert (got["rgb0"] - gold["rgb0"]).abs().max().item() <= 5e-5            # the coarse pass is fp32-class here too
     assert st["err_p50"] <= 3e-4 and st["err_p99"] <= 1.5e-2, st
     assert st["frac_rays_within_3e-2"] >= 0.99, st
-    flips = (got["acc_map"].reshape(-1) - gold["acc_map"].reshape(-1)).abs() > 0.5
-    assert flips.sum().item() <= 4 and bool((inp["sigma_last"][flips].abs() < 2e-2).all()), inp["sigma_last"][flips]
-    assert st["max_abs_rgb_excluding_gate_flips"] <= 8e-2 and st["psnr_db_excluding_gate_flips"] >= 50.0, st
+    # a flip = the sign of sigma at the last sample differs from the reference's: only where the reference's own value
+    # is within the fp16 chain's rounding of zero
+    assert st["opacity_gate_flips"] <= n // 100 and st["gate_flip_max_abs_sigma_last_of_reference"] < 2e-2, st
+    assert st["max_abs_rgb_excluding_gate_flips"] <= 6e-2 and st["psnr_db_excluding_gate_flips"] >= 50.0, st
 
 
 def test_frame_sample_error_distribution_with_the_references_own_yardsticks():
@@ -429,7 +433,8 @@ def test_frame_sample_error_distribution_with_the_references_own_yardsticks():
             ref = O.render_rays(rays, cg, fg, shape.to(DEV), em, tex.to(DEV), N_samples=64, N_importance=64,
                                 netchunk=196608, retraw=True)
             torch.backends.cuda.matmul.allow_tf32 = True
-            tf = O.render_rays(rays, cg, fg, shape.to(DEV), em, tex.to(DEV), N_samples=64, N_importance=64, netchunk=196608)
+            tf = O.render_rays(rays, cg, fg, shape.to(DEV), em, tex.to(DEV), N_samples=64, N_importance=64, netchunk=196608,
+                               retraw=True)
     finally:
         torch.backends.cuda.matmul.allow_tf32 = prev
     from mofanerf_b200 import B200Renderer
@@ -439,9 +444,10 @@ def test_frame_sample_error_distribution_with_the_references_own_yardsticks():
         rgb, disp, acc, extras = r.render_fitting(
             1, n, None, chunk=1 << 30, rays=(ro[idx].to(DEV), rd[idx].to(DEV)), shapeCodes=shape.to(DEV),
             uvCodes=tex.to(DEV), expType=20, expCodes=exp.to(DEV), near=8.0, far=26.0, use_viewdirs=True, ndc=False,
-            network_fn=cg, network_fine=fg, N_samples=64, N_importance=64, perturb=0.0, raw_noise_std=0.0)
-    st = bench.parity_stats(rgb, acc, ref["rgb_map"], ref["acc_map"])
-    yt = bench.parity_stats(tf["rgb_map"], tf["acc_map"], ref["rgb_map"], ref["acc_map"])
+            network_fn=cg, network_fine=fg, N_samples=64, N_importance=64, perturb=0.0, raw_noise_std=0.0, retraw=True)
+    last = lambda raw: raw.reshape(n, -1, 4)[:, -1, 3]
+    st = bench.parity_stats(rgb, acc, ref["rgb_map"], ref["acc_map"], last(extras["raw"]), last(ref["raw"]))
+    yt = bench.parity_stats(tf["rgb_map"], tf["acc_map"], ref["rgb_map"], ref["acc_map"], last(tf["raw"]), last(ref["raw"]))
     for tag, d in (("engine_vs_fp32", st), ("reference_tf32_vs_fp32", yt)):
         parity_log.record("frame_sample_4096_" + tag, rays=n, **{k: v for k, v in d.items()})
     print(f"[parity] frame sample: engine {st}\n[parity] frame sample: TF32 reference {yt}")
@@ -450,10 +456,9 @@ def test_frame_sample_error_distribution_with_the_references_own_yardsticks():
     # the distribution (measured on 8192 rays: p50 1.1e-4, p99 7.5e-3, 99.87 % of rays within 3e-2, 57 dB without the flips)
     assert st["err_p50"] <= 3e-4 and st["err_p99"] <= 1.5e-2, st
     assert st["frac_rays_within_3e-2"] >= 0.995, st
-    assert st["max_abs_rgb_excluding_gate_flips"] <= 8e-2 and st["psnr_db_excluding_gate_flips"] >= 50.0, st
-    # every opacity-gate flip is a ray whose REFERENCE sigma at the last sample is within rounding of zero
-    flips = (acc.reshape(-1) - ref["acc_map"].reshape(-1)).abs() > 0.5
-    sig_last = ref["raw"].reshape(n, -1, 4)[:, -1, 3]
-    assert flips.sum().item() <= 8 and bool((sig_last[flips].abs() < 2e-2).all()), sig_last[flips]
+    assert st["max_abs_rgb_excluding_gate_flips"] <= 6e-2 and st["psnr_db_excluding_gate_flips"] >= 50.0, st
+    # every opacity-gate flip (sign of sigma at the last sample differs) is a ray whose REFERENCE sigma there is within
+    # the fp16 chain's rounding of zero
+    assert st["opacity_gate_flips"] <= n // 100 and st["gate_flip_max_abs_sigma_last_of_reference"] < 2e-2, st
     # the engine is at least as close to the fp32 reference as the reference's own TF32 mode (measured: 3x closer)
     assert st["mean_abs_rgb"] <= yt["mean_abs_rgb"] and st["err_p99"] <= yt["err_p99"], (st, yt)

@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--thr", type=float, default=0.02)
     ap.add_argument("--n-samples", type=int, default=64)
     ap.add_argument("--n-importance", type=int, default=64)
+    ap.add_argument("--seed", type=int, default=0, help="seed of the nets (0 = bench.py's; 5 = the fixtures' dense field)")
     ap.add_argument("--sigma-gain", type=float, default=1.0,
                     help="scale alpha_linear (weight and bias) of both nets: a sharper density field, sigma further from 0")
     args = ap.parse_args()
@@ -36,13 +37,13 @@ def main():
     from oracle import mofa_oracle as O
 
     dev = torch.device("cuda:0")
-    c, f, s = O.build_nets(0)
+    c, f, s = O.build_nets(args.seed)
     shape, tex, exp, ro, rd = bench.synth_inputs(args.H, args.W)
     n = min(args.rays, ro.shape[0])
     idx = torch.linspace(0, ro.shape[0] - 1, n).long()
     ro_s, rd_s = ro[idx], rd[idx]
     rays_cpu = O.make_ray_batch(ro_s, rd_s, 8.0, 26.0)
-    cg, fg, sg = O.build_nets(0)
+    cg, fg, sg = O.build_nets(args.seed)
     if args.sigma_gain != 1.0:
         with torch.no_grad():
             for net in (c, f, cg, fg):
@@ -95,11 +96,12 @@ def main():
     sig_min = ref["raw"].reshape(n, -1, 4)[..., 3].abs().min(dim=1).values
     flips = (a["acc_map"].reshape(-1) - ref["acc_map"]).abs() > 0.5
     stats = {
-        "engine_vs_fp32": bench.parity_stats(a["rgb_map"], a["acc_map"], ref["rgb_map"], ref["acc_map"]),
+        "engine_vs_fp32": bench.parity_stats(a["rgb_map"], a["acc_map"], ref["rgb_map"], ref["acc_map"],
+                                             a["raw"].reshape(n, -1, 4)[:, -1, 3], sig_last),
         "tf32_vs_fp32": bench.parity_stats(ref_tf["rgb_map"], ref_tf["acc_map"], ref["rgb_map"], ref["acc_map"]),
         "fp32_netchunk65536_vs_fp32": bench.parity_stats(ref_nc["rgb_map"], ref_nc["acc_map"], ref["rgb_map"], ref["acc_map"]),
         "engine_vs_tf32": bench.parity_stats(a["rgb_map"], a["acc_map"], ref_tf["rgb_map"], ref_tf["acc_map"]),
-        "sigma_gain": args.sigma_gain,
+        "sigma_gain": args.sigma_gain, "net_seed": args.seed,
         "ref_acc_quantiles": {str(q): float(torch.quantile(ref["acc_map"], q)) for q in (0.01, 0.05, 0.25, 0.5)},
         "frac_ref_acc_below_0.3": float((ref["acc_map"] < 0.3).float().mean()),
         "bad_rays_with_ref_acc_below_0.3": int((ref["acc_map"][bad] < 0.3).sum()),
