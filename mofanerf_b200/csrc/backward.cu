@@ -155,22 +155,44 @@ cudaError_t launch_view_head_bwd(const float* d_raw, const float* w_rgb, const _
   return cudaGetLastError();
 }
 
-// out[n] += sum_p dZ[p, n]     grid (N/64, row blocks of 2048); block 256 = 64 columns x 4 row phases
-__global__ void colsum_kernel(const __half* __restrict__ dZ, int N, int64_t P, float* __restrict__ out) {
-  // 256 threads = 32 column PAIRS (one 128-byte row segment per warp and load) x 8 row phases
+// out[n] += sum_p dZ[p, n]     grid (N/64, row blocks of 2048); block 256 = 8 column groups x 32 row phases
+// 16-byte row segments: lane & 7 selects 8 of the block's 64 columns, the other thread bits one of 32 row phases — a warp
+// load covers four whole 128-byte lines, four loads are in flight per thread.  (2-byte-per-thread loads with one row per
+// iteration ran at 4 TB/s: 12 % of a training step went into these column sums.)
+__device__ __forceinline__ void add8(float (&a)[8], const uint4 v) {
+  const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
+  const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+  const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&v.z));
+  const float2 f3 = __half22float2(*reinterpret_cast<const __half2*>(&v.w));
+  a[0] += f0.x; a[1] += f0.y; a[2] += f1.x; a[3] += f1.y; a[4] += f2.x; a[5] += f2.y; a[6] += f3.x; a[7] += f3.y;
+}
+
+__global__ void __launch_bounds__(256) colsum_kernel(const __half* __restrict__ dZ, int N, int64_t P, float* __restrict__ out) {
   __shared__ float red[8][64];
-  const int cp = threadIdx.x & 31, ph = threadIdx.x >> 5;
-  const int col = blockIdx.x * 64 + 2 * cp;
+  const int cg = threadIdx.x & 7, rp = threadIdx.x >> 3;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t r0 = static_cast<int64_t>(blockIdx.y) * 2048;
   const int64_t r1 = (r0 + 2048 < P) ? r0 + 2048 : P;
-  float a0 = 0.f, a1 = 0.f;
-  for (int64_t r = r0 + ph; r < r1; r += 8) {
-    const float2 v = __half22float2(*reinterpret_cast<const __half2*>(dZ + r * N + col));
-    a0 += v.x;
-    a1 += v.y;
+  const __half* base = dZ + blockIdx.x * 64 + cg * 8;
+  float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  int64_t r = r0 + rp;
+  for (; r + 96 < r1; r += 128) {
+    const uint4 v0 = __ldg(reinterpret_cast<const uint4*>(base + r * N));
+    const uint4 v1 = __ldg(reinterpret_cast<const uint4*>(base + (r + 32) * N));
+    const uint4 v2 = __ldg(reinterpret_cast<const uint4*>(base + (r + 64) * N));
+    const uint4 v3 = __ldg(reinterpret_cast<const uint4*>(base + (r + 96) * N));
+    add8(a, v0); add8(a, v1); add8(a, v2); add8(a, v3);
   }
-  red[ph][2 * cp] = a0;
-  red[ph][2 * cp + 1] = a1;
+  for (; r < r1; r += 32) add8(a, __ldg(reinterpret_cast<const uint4*>(base + r * N)));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {       // the four row phases of a warp hold the same columns
+    a[i] += __shfl_xor_sync(0xffffffffu, a[i], 8);
+    a[i] += __shfl_xor_sync(0xffffffffu, a[i], 16);
+  }
+  if (lane < 8) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[warp][lane * 8 + i] = a[i];
+  }
   __syncthreads();
   if (threadIdx.x < 64) {
     float t = 0.f;
@@ -331,31 +353,83 @@ cudaError_t launch_outer_add(const float* u, const float* v, int rows, int cols,
 
 // Head weight gradients: gW[q, c] += a * sum_p g[p*4 + q0 + q] * act[p, c];  gb[q] += a * sum_p g[p*4 + q0 + q]
 // grid (N/64, row blocks of 2048); 256 threads = 64 columns x 4 row phases
-__global__ void head_wgrad_kernel(const float* __restrict__ g, int q0, int nq, const __half* __restrict__ act, int N,
+__global__ void __launch_bounds__(256) head_wgrad_kernel(const float* __restrict__ g, int q0, int nq, const __half* __restrict__ act, int N,
                                   int64_t P, float a_h, float* __restrict__ gW, float* __restrict__ gb,
                                   const float* __restrict__ sc) {
+  // same thread layout as colsum_kernel (16-byte activation loads, 32 row phases, two rows in flight per thread); the
+  // upstream gradient row g[r, 0..3] is one 16-byte broadcast load per row
   const float a = a_h * (sc ? __ldg(sc) : 1.0f);
-  __shared__ float red[4][3][64];
-  const int c = threadIdx.x & 63, ph = threadIdx.x >> 6;
-  const int col = blockIdx.x * 64 + c;
+  __shared__ float red[8][3][64];
+  __shared__ float redb[8][3];
+  const int cg = threadIdx.x & 7, rp = threadIdx.x >> 3;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t r0 = static_cast<int64_t>(blockIdx.y) * 2048;
   const int64_t r1 = (r0 + 2048 < P) ? r0 + 2048 : P;
-  float acc[3] = {0.f, 0.f, 0.f}, accb[3] = {0.f, 0.f, 0.f};
-  for (int64_t r = r0 + ph; r < r1; r += 4) {
-    const float x = __half2float(act[r * N + col]);
+  const __half* base = act + blockIdx.x * 64 + cg * 8;
+  float acc[3][8], accb[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int q = 0; q < 3; ++q)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[q][i] = 0.f;
+  auto row = [&](const uint4 v, const float4 g4) {
+    float x[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    add8(x, v);
+    const float gq[3] = {q0 == 3 ? g4.w : g4.x, g4.y, g4.z};    // (q0, nq) is (3, 1) for alpha_linear, (0, 3) for rgb_linear
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      if (q >= nq) break;
+      const float gv = gq[q];
+      accb[q] += gv;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[q][i] += gv * x[i];
+    }
+  };
+  int64_t r = r0 + rp;
+  for (; r + 32 < r1; r += 64) {
+    const uint4 v0 = __ldg(reinterpret_cast<const uint4*>(base + r * N));
+    const uint4 v1 = __ldg(reinterpret_cast<const uint4*>(base + (r + 32) * N));
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(g + r * 4));
+    const float4 g1 = __ldg(reinterpret_cast<const float4*>(g + (r + 32) * 4));
+    row(v0, g0);
+    row(v1, g1);
+  }
+  for (; r < r1; r += 32)
+    row(__ldg(reinterpret_cast<const uint4*>(base + r * N)), __ldg(reinterpret_cast<const float4*>(g + r * 4)));
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      acc[q][i] += __shfl_xor_sync(0xffffffffu, acc[q][i], 8);
+      acc[q][i] += __shfl_xor_sync(0xffffffffu, acc[q][i], 16);
+    }
+    accb[q] += __shfl_xor_sync(0xffffffffu, accb[q], 8);     // every column group of a row phase saw the same g rows
+    accb[q] += __shfl_xor_sync(0xffffffffu, accb[q], 16);
+  }
+  if (lane < 8) {
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) red[warp][q][lane * 8 + i] = acc[q][i];
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int q = 0; q < 3; ++q) redb[warp][q] = accb[q];
+  }
+  __syncthreads();
+  if (threadIdx.x < 64) {
     for (int q = 0; q < nq; ++q) {
-      const float gq = g[r * 4 + q0 + q];
-      acc[q] += gq * x;
-      accb[q] += gq;
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += red[w][q][threadIdx.x];
+      atomicAdd(gW + static_cast<size_t>(q) * N + blockIdx.x * 64 + threadIdx.x, a * t);
     }
   }
-  for (int q = 0; q < 3; ++q) red[ph][q][c] = acc[q];
-  __syncthreads();
-  if (ph == 0)
-    for (int q = 0; q < nq; ++q)
-      atomicAdd(gW + static_cast<size_t>(q) * N + col, a * (red[0][q][c] + red[1][q][c] + red[2][q][c] + red[3][q][c]));
-  if (blockIdx.x == 0 && c == 0)   // bias: every row phase of the first column block adds its partial
-    for (int q = 0; q < nq; ++q) atomicAdd(gb + q, a * accb[q]);
+  if (blockIdx.x == 0 && threadIdx.x < nq) {     // bias: rows of this block, counted once (first column block only)
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += redb[w][threadIdx.x];
+    atomicAdd(gb + threadIdx.x, a * t);
+  }
 }
 cudaError_t launch_head_wgrad(const float* g, int q0, int nq, const __half* act, int N, int64_t P, float a, float* gW,
                               float* gb, cudaStream_t s, const float* sc) {

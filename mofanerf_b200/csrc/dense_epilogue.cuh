@@ -35,6 +35,12 @@ __device__ __forceinline__ float4 ldg_f4_pinned(const float4* ptr) {
   return r;
 }
 
+__device__ __forceinline__ uint4 ldg_u4_pinned(const uint4* ptr) {
+  uint4 r;
+  asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(ptr));
+  return r;
+}
+
 // One epilogue GROUP = 4 warps (one per TMEM lane quadrant) that own a range of 64-column blocks of the tile, their
 // own staging buffer(s), their own named barrier and their own head slot.  The single-CTA kernel and the 4-warp pair
 // kernel run one group over all BN columns; the 8-warp pair kernel runs two groups on one half of the columns each.
@@ -59,6 +65,19 @@ __device__ __forceinline__ void epilogue_tile_impl(const EpiParams& p, const voi
                                                    long long hrow0) {
   float hacc[3] = {0.f, 0.f, 0.f};
   const float r1 = (BWD && p.r1_row != nullptr && m0 + row < p.M) ? p.r1_row[static_cast<size_t>(m0 + row) * p.r1_stride] : 0.0f;
+  // Backward: the ReLU mask of a 32-column chunk (this row's 64 bytes of the forward activation, which comes from HBM —
+  // the tensor is far larger than L2) is fetched ONE CHUNK AHEAD, while the previous chunk is being processed.  Fetched
+  // where it is used (inside the 8-column loop) every block exposed a full memory latency: the dX kernel ran 47 % longer
+  // than the forward kernel of the same layer.
+  const bool use_mask = BWD && p.mask != nullptr && m0 + row < p.M;
+  const __half* mrow = use_mask ? p.mask + static_cast<size_t>(m0 + row) * p.N + n0 : nullptr;
+  uint4 mk_cur[4], mk_nxt[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) mk_cur[j] = mk_nxt[j] = make_uint4(0x3c003c00u, 0x3c003c00u, 0x3c003c00u, 0x3c003c00u);   // fp16 ones: keep everything
+  if (use_mask) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) mk_cur[j] = ldg_u4_pinned(reinterpret_cast<const uint4*>(mrow + g.cb0 * 64) + j);
+  }
 #pragma unroll 1
   for (int cb = g.cb0; cb < g.cb1; ++cb) {
     const uint32_t cbuf = g.cbuf0 + (NBUF == 2 ? (cnt & 1u) * (128 * 64 * 2) : 0u);
@@ -71,6 +90,13 @@ __device__ __forceinline__ void epilogue_tile_impl(const EpiParams& p, const voi
       uint32_t v[32];
       tmem_ld_32x32b_x32(acc_addr + cb * 64 + h * 32, v);
       const int ncol = n0 + cb * 64 + h * 32;
+      if (use_mask) {       // next chunk of this row: the other half of the block, or the first half of the next block
+        const int nxt = cb * 64 + h * 32 + 32;
+        if (nxt < g.cb1 * 64) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) mk_nxt[j] = ldg_u4_pinned(reinterpret_cast<const uint4*>(mrow + nxt) + j);
+        }
+      }
       // head weights: HEAD == 1 fetches the whole 32-column chunk here (32 registers); HEAD == 3 would need 96, so it
       // fetches one 8-column block ahead of the block being reduced (two rotating sets of 24 registers)
       constexpr int HB = (HEAD == 3) ? 1 : 4;           // 8-column blocks per fetch
@@ -101,9 +127,7 @@ __device__ __forceinline__ void epilogue_tile_impl(const EpiParams& p, const voi
           bb[0] += r1 * c0.x; bb[1] += r1 * c0.y; bb[2] += r1 * c0.z; bb[3] += r1 * c0.w;
           bb[4] += r1 * c1.x; bb[5] += r1 * c1.y; bb[6] += r1 * c1.z; bb[7] += r1 * c1.w;
         }
-        uint4 mk = make_uint4(0x3c003c00u, 0x3c003c00u, 0x3c003c00u, 0x3c003c00u);   // fp16 ones: keep everything
-        if (BWD && p.mask != nullptr && m0 + row < p.M)
-          mk = __ldg(reinterpret_cast<const uint4*>(p.mask + static_cast<size_t>(m0 + row) * p.N + ncol) + j);
+        const uint4 mk = mk_cur[j];
         const __half* mh = reinterpret_cast<const __half*>(&mk);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
@@ -143,6 +167,10 @@ __device__ __forceinline__ void epilogue_tile_impl(const EpiParams& p, const voi
                        "r"(*reinterpret_cast<uint32_t*>(&h2)), "r"(*reinterpret_cast<uint32_t*>(&h3))
                        : "memory");
         }
+      }
+      if constexpr (BWD) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) mk_cur[j] = mk_nxt[j];
       }
     }
     if (p.store_c) {

@@ -220,11 +220,24 @@ cudaError_t launch_wgrad_tc(const WgradLaunch& W, int num_sms, cudaStream_t stre
   p.kb_total = static_cast<int>(W.P / 64);
   const int tiles_mn = p.m_tiles * p.n_tiles;
   if (tiles_mn <= 0 || p.kb_total <= 0) return cudaSuccess;
-  // enough splits of the reduction to fill the machine, at least 8 K-blocks (512 rows) each
-  int splits = (num_sms + tiles_mn - 1) / tiles_mn;
+  // Splits of the reduction: the persistent grid runs ceil(tiles / num_sms) rounds of tiles, each as long as one split,
+  // so the split count is chosen to minimise  rounds x (K-blocks per split + epilogue)  — not just "enough tiles to fill
+  // the machine": a 1024 x 1024 gradient has 32 output tiles, and 5 splits (160 tiles on 148 SMs) meant two rounds of 410
+  // K-blocks where 9 splits give two rounds of 228.  At least 8 K-blocks (512 rows) per split; the epilogue (a 128 x BN
+  // fp32 red.add per tile) is charged as 8 K-blocks.
   const int max_splits = (p.kb_total + 7) / 8;
-  if (splits > max_splits) splits = max_splits;
-  if (splits < 1) splits = 1;
+  int splits = 1;
+  long long best = -1;
+  for (int s = 1; s <= max_splits && s <= num_sms; ++s) {
+    const int per = (p.kb_total + s - 1) / s;
+    const int eff = (p.kb_total + per - 1) / per;            // splits that actually get work
+    const long long rounds = (static_cast<long long>(tiles_mn) * eff + num_sms - 1) / num_sms;
+    const long long cost = rounds * (per + 8);
+    if (best < 0 || cost < best) {
+      best = cost;
+      splits = s;
+    }
+  }
   p.kb_per_split = (p.kb_total + splits - 1) / splits;
   p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
   const int tiles = tiles_mn * p.splits;
