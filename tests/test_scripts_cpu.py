@@ -99,3 +99,189 @@ lrate = 5e-5
     assert all(c[2] == 32 and c[3] == 0 and c[4] == 0.0 and c[6] == 12 for c in rr)
     assert ("set_latents", 50, 30, 256) in fake.calls
     assert any(c[0] == "load_network" and c[2] == "DataParallel" for c in fake.calls)     # run_fit.py:166-167
+
+
+EXPRESSIONS = ["neutral", "smile", "mouth_stretch", "anger", "jaw_left", "jaw_right", "jaw_forward", "mouth_left",
+               "mouth_right", "dimpler", "chin_raiser", "lip_puckerer", "lip_funneler", "sadness", "lip_roll", "grin",
+               "cheek_blowing", "eye_closed", "brow_raiser", "brow_lower"]       # render_refine_trainSet.py:147-150
+
+
+def _write_facescape_like_dataset(root, person="1", n_train=2000, hw=32, all_images=False):
+    """A synthetic stand-in for the FaceScape multi-view set the scripts read (run_train.py:26-90,
+    render_refine_trainSet.py:38-108): transforms_{train,val,test}_<id>.json with 100 views x 20 expressions for one
+    person, ONE real image file (the loaders open only the first to learn H, W), and the directory entries
+    getValidPerson() looks up by name (render_refine_trainSet.py:131-143)."""
+    import json
+    from PIL import Image
+    ds = root / "ds"
+    ds.mkdir(parents=True)
+    for name in [person, "39", "52", "69", "295", "307", "413", "417", "587", "237", "353", "356", "440", "363"]:
+        (ds / name).mkdir(exist_ok=True)
+    (ds / person / "neutral").mkdir()
+    Image.fromarray((np.random.RandomState(1).rand(hw, hw, 4) * 255).astype(np.uint8)).save(ds / person / "neutral" / "000.png")
+    from oracle import mofa_oracle as O
+
+    def frames(n):
+        out = []
+        for k in range(n):
+            c2w = O.pose_spherical(-60.0 + 1.2 * (k % 100), 0.0, 16.0).numpy().tolist()
+            out.append({"file_path": f"/{person}/{EXPRESSIONS[(k // 100) % 20]}/{k % 100:03d}", "transform_matrix": c2w,
+                        "expression": (k // 100) % 20})
+        return out
+    for split, n in (("train", n_train), ("val", 1), ("test", 1)):
+        with open(ds / f"transforms_{split}_{person}.json", "w") as fp:
+            json.dump({"camera_angle_x": 0.45, "frames": frames(n)}, fp)
+    if all_images:        # run_train.py reads the image of whichever training frame it draws (:278-281)
+        for k, fr in enumerate(frames(n_train)):
+            f = ds / (fr["file_path"][1:] + ".png")
+            f.parent.mkdir(parents=True, exist_ok=True)
+            if not f.exists():
+                Image.fromarray((np.random.RandomState(10 + k).rand(hw, hw, 4) * 255).astype(np.uint8)).save(f)
+    return ds
+
+
+def _common_cfg(tmp_path, ds, extra=""):
+    cfg = tmp_path / "cfg.txt"
+    cfg.write_text(f"""expname = plumb
+basedir = {tmp_path}/logs
+datadir = {ds}
+dataset_type = blender
+personList = 1
+no_batching = True
+netchunk = 4096
+chunk = 4096
+use_viewdirs = True
+white_bkgd = False
+N_samples = 16
+N_importance = 16
+N_rand = 64
+netwidth = 256
+netwidth_fine = 256
+netdepth_fine = 8
+testskip = 1
+input_ch_shapeCodes = 50
+input_ch_textureCodes = 256
+input_ch_expCodes = 30
+lrate = 5e-5
+{extra}""")
+    return cfg
+
+
+def test_render_refine_trainset_runs_unchanged_under_the_launcher(tmp_path, monkeypatch):
+    """BASELINE config #5's script, UNCHANGED (render_refine_trainSet.py:146-311): one identity of a synthetic
+    FaceScape-like set -> 10 expressions x 8 views through render_path -> render -> texture encoder -> (fake) engine ->
+    80 PNG files in the directory layout the refine-net training set expects.  The script has no exit condition of its
+    own other than running out of identities (it indexes images[i] for 300 persons): the synthetic set has one, so the
+    run ends with the IndexError of person #3 — after person #1 is complete and person #2's slot was skipped as done."""
+    from mofanerf_b200 import launch, renderer
+    from tests.fake_engine import FakeEngine
+    ref_loader.load()
+    fake = FakeEngine()
+    monkeypatch.setattr(renderer, "get_engine", lambda device=None: fake)
+    monkeypatch.setattr(renderer.B200Renderer, "_to_device", lambda self, rays: rays)
+    monkeypatch.setattr(torch, "set_default_tensor_type", lambda t: None)
+    ds = _write_facescape_like_dataset(tmp_path)
+    work = tmp_path / "work"
+    (work / "data").mkdir(parents=True)
+    np.save(work / "data" / "factors_id.npy", np.random.RandomState(2).randn(4, 50).astype(np.float32) * 0.03)   # load_bmData (:126)
+    cfg = _common_cfg(tmp_path, ds)
+    # the script reads every identity's UV map from an absolute path of its authors' machine (:287): serve it from memory
+    launch.shim_missing_modules()
+    import imageio
+    real_imread = imageio.imread
+    uv = (np.random.RandomState(3).rand(64, 64, 3) * 255).astype(np.uint8)
+    monkeypatch.setattr(imageio, "imread", lambda p, *a, **k: uv if str(p).startswith("/data/myNerf/") else real_imread(p, *a, **k))
+    cwd, argv = os.getcwd(), list(sys.argv)
+    import models.render_class as rc
+    orig_renderer = rc.myRenderer
+    os.chdir(work)
+    try:
+        with pytest.raises(IndexError):
+            launch.main(["--shim-missing", "--no-chdir", os.path.join(ref_loader.REF_ROOT, "render_refine_trainSet.py"),
+                         "--config", str(cfg)])
+    finally:
+        os.chdir(cwd)
+        sys.argv = argv
+        rc.myRenderer = orig_renderer
+    out = tmp_path / "logs" / "plumb_1" / "renderonly_path_000000" / "rf_trainSet" / "train" / "1"
+    exps = sorted(p.name for p in out.iterdir())
+    assert len(exps) == 10 and set(exps) <= set(EXPRESSIONS)                  # num_exp_type (:246)
+    pngs = sorted(out.glob("*/*.png"))
+    assert len(pngs) == 80                                                     # x num_images_per_exp (:247)
+    from PIL import Image
+    assert Image.open(pngs[0]).size == (16, 16)                                # half_res of the 32x32 set (:167)
+    rr = [c for c in fake.calls if c[0] == "render_rays"]
+    assert len(rr) == 80 and all(c[1] == 256 and c[2] == 16 and c[3] == 16 and c[4] == 0.0 for c in rr)
+    assert sum(1 for c in fake.calls if c == ("set_latents", 50, 30, 256)) == 80   # a new identity / expression / texture per image
+    lines = (tmp_path / "logs" / "plumb_1" / "renderonly_path_000000" / "renderImageList.txt").read_text().splitlines()
+    assert len(lines) == 80
+
+
+def test_run_train_iterations_run_unchanged_under_the_launcher(tmp_path, monkeypatch):
+    """run_train.py UNCHANGED (:160-405) for two optimisation steps on a synthetic FaceScape-like set: data loading,
+    create_nerf, DataParallel wrapping (:253-257), landmark-guided ray sampling, render(rays=..., uvMap=..., retraw=True,
+    perturb=1) in TRAINING mode through the drop-in renderer's autograd node, the rgb + rgb0 loss, backward, Adam step.
+    The engine is the recording fake (no GPU here): it hands back constant gradients, so what is checked is that the
+    script's loss reaches the engine's backward with weight gradients requested for both networks, and that the
+    optimiser then moves the NeRF weights, the texture encoder, the StyleModule and the expression code it used."""
+    from mofanerf_b200 import launch, renderer
+    from tests.fake_engine import FakeEngine
+    ref_loader.load()
+    fake = FakeEngine()
+    fake.stop_after_train_renders = 2
+    monkeypatch.setattr(renderer, "get_engine", lambda device=None: fake)
+    monkeypatch.setattr(renderer.B200Renderer, "_to_device", lambda self, rays: rays)
+    monkeypatch.setattr(torch, "set_default_tensor_type", lambda t: None)
+    ds = _write_facescape_like_dataset(tmp_path, n_train=4, all_images=True)
+    work = tmp_path / "work" / "repo"                      # the script reads ../data/... relative to its working directory
+    work.mkdir(parents=True)
+    data = tmp_path / "work" / "data"
+    (data / "textureMap300" / "1").mkdir(parents=True)
+    np.save(data / "factors_id.npy", np.random.RandomState(2).randn(4, 50).astype(np.float32) * 0.03)      # load_bmData (:120)
+    np.save(data / "1_975_landmarks.npy", np.random.RandomState(4).randn(4, 20, 68, 3).astype(np.float32))    # LMModule (:126)
+    from PIL import Image
+    Image.fromarray((np.random.RandomState(3).rand(64, 64, 3) * 255).astype(np.uint8)).save(data / "textureMap300" / "1" / "1_neutral.jpg")
+    cfg = _common_cfg(tmp_path, ds, extra="i_print = 1\n")
+    captured = {}
+    import tools.create_model_condition as cmc
+    real_create = cmc.create_nerf
+
+    def spy_create(args):
+        res = real_create(args)
+        captured["train_kwargs"], captured["render"], captured["optimizer"] = res[0], res[6], res[4]
+        captured["before"] = {
+            "coarse": res[0]["network_fn"].alpha_linear[0].weight.detach().clone(),
+            "fine": res[0]["network_fine"].alpha_linear[0].weight.detach().clone(),
+            "tex": next(res[6].texEncoder.parameters()).detach().clone(),
+            "style": next(res[6].idSpecificMod.parameters()).detach().clone(),
+            "exp": [c.detach().clone() for c in res[6].expCodes_Sigma],
+        }
+        return res
+    monkeypatch.setattr(cmc, "create_nerf", spy_create)
+    cwd, argv = os.getcwd(), list(sys.argv)
+    import models.render_class as rc
+    orig_renderer = rc.myRenderer
+    os.chdir(work)
+    try:
+        with pytest.raises(FakeEngine.Stop):
+            launch.main(["--shim-missing", "--no-chdir", os.path.join(ref_loader.REF_ROOT, "run_train.py"),
+                         "--config", str(cfg)])
+    finally:
+        os.chdir(cwd)
+        sys.argv = argv
+        rc.myRenderer = orig_renderer
+    fwd = [c for c in fake.calls if c[0] == "render_rays"]
+    bwd = [c for c in fake.calls if c[0] == "render_rays_bwd"]
+    assert len(fwd) == 2 and all(c[-1] == "train" and c[1] == 64 and c[2] == 16 and c[3] == 16 and c[4] == 1.0 for c in fwd)
+    # both losses (rgb and rgb0, run_train.py:341-346) reach the backward; weight gradients of both nets are requested
+    assert len(bwd) == 2 and all(c[2] and c[3] and c[4] > 90 for c in bwd), bwd
+    kw, rend, before = captured["train_kwargs"], captured["render"], captured["before"]
+    assert type(rend).__name__ == "B200Renderer"
+    coarse = getattr(kw["network_fn"], "module", kw["network_fn"])
+    fine = getattr(kw["network_fine"], "module", kw["network_fine"])
+    assert not torch.equal(coarse.alpha_linear[0].weight, before["coarse"])
+    assert not torch.equal(fine.alpha_linear[0].weight, before["fine"])
+    assert not torch.equal(next(rend.texEncoder.parameters()), before["tex"])
+    assert not torch.equal(next(rend.idSpecificMod.parameters()), before["style"])
+    assert any(not torch.equal(a, b) for a, b in zip(rend.expCodes_Sigma, before["exp"]))
+    assert (tmp_path / "logs" / "plumb_1" / "args.txt").exists()
