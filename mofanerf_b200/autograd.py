@@ -17,6 +17,10 @@ import torch
 class RenderRaysFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, rays, shape, exp_mod, tex, engine, cfg, *params):
+        # outputs the loss does not use arrive in backward as None instead of zero tensors: run_fit.py's loss is on
+        # rgb_map only (:309), so the whole coarse-pass backward (rgb0 / acc0) is skipped there — the engine skips a pass
+        # whose upstream gradients are both absent
+        ctx.set_materialize_grads(False)
         engine.set_latents(shape, exp_mod, tex)
         out = engine.render_rays(rays.detach(), cfg["N_samples"], cfg["N_importance"], run_fine=cfg["run_fine"],
                                  fine_net=cfg["fine_net"], perturb=cfg["perturb"], raw_noise_std=cfg["raw_noise_std"],

@@ -285,3 +285,52 @@ def test_run_train_iterations_run_unchanged_under_the_launcher(tmp_path, monkeyp
     assert not torch.equal(next(rend.idSpecificMod.parameters()), before["style"])
     assert any(not torch.equal(a, b) for a, b in zip(rend.expCodes_Sigma, before["exp"]))
     assert (tmp_path / "logs" / "plumb_1" / "args.txt").exists()
+
+
+def test_run_fit_fitting_iterations_run_unchanged_under_the_launcher(tmp_path, monkeypatch):
+    """BASELINE config #3's script flow, UNCHANGED: `run_fit.py --renderType fitting --num_iterations 6` (:257-350; the
+    script divides by num_iterations // 6) — seven iterations of landmark-guided ray sampling from a differentiable pose (get_rays_withGrad), render_fitting with
+    requires_grad pose / shape / texture / expression codes through the drop-in renderer's autograd node, L1 loss, three Adam
+    optimisers; plus the parameter file and the preview image the script writes at iteration 0.  The recording fake stands
+    in for the engine (constant gradients): checked is that the nets stay in eval mode (no weight gradients requested,
+    models/render_class.py:383-384), that every iteration reaches the engine's backward, and what lands on disk."""
+    from mofanerf_b200 import launch, renderer
+    from tests.fake_engine import FakeEngine
+    ref_loader.load()
+    fake = FakeEngine()
+    monkeypatch.setattr(renderer, "get_engine", lambda device=None: fake)
+    monkeypatch.setattr(renderer.B200Renderer, "_to_device", lambda self, rays: rays)
+    monkeypatch.setattr(torch, "set_default_tensor_type", lambda t: None)
+    data = tmp_path / "data" / "segRelRes"
+    data.mkdir(parents=True)
+    from PIL import Image
+    Image.fromarray((np.random.RandomState(0).rand(512, 512, 3) * 200 + 30).astype(np.uint8)).save(data / "00002.png")
+    rs = np.random.RandomState(5)
+    kp = np.stack([200 + 110 * rs.rand(68), 200 + 110 * rs.rand(68)], 1).astype(np.float32)      # 68 landmarks inside the face box
+    from oracle import mofa_oracle as O
+    np.save(tmp_path / "data" / "pose_00002.npy", {"pose": O.pose_spherical(10.0, 0.0, 16.0).numpy(), "kp": kp}, allow_pickle=True)
+    cfg = _common_cfg(tmp_path, tmp_path / "data", extra="person_num = 300\n")
+    cwd, argv = os.getcwd(), list(sys.argv)
+    import models.render_class as rc
+    orig_renderer = rc.myRenderer
+    try:
+        launch.main(["--shim-missing", os.path.join(ref_loader.REF_ROOT, "run_fit.py"), "--config", str(cfg),
+                     "--filePath", str(data / "00002.png"), "--renderType", "fitting", "--num_iterations", "6"])
+    finally:
+        os.chdir(cwd)
+        sys.argv = argv
+        rc.myRenderer = orig_renderer
+    fwd = [c for c in fake.calls if c[0] == "render_rays"]
+    bwd = [c for c in fake.calls if c[0] == "render_rays_bwd"]
+    train_fwd = [c for c in fwd if c[-1] == "train"]
+    assert len(train_fwd) == 7 and all(c[1] == 64 and c[2] == 16 and c[3] == 16 and c[4] == 0.0 for c in train_fwd)
+    assert len(bwd) == 7 and all(c[2] and not c[3] and c[4] == 0 for c in bwd), bwd      # rgb loss only, weights are constants
+    out = tmp_path / "data" / "fitting" / "segRelRes_00002"
+    assert (out / "target.png").exists()
+    prev = out / "segRelRes_00002_0.png"                     # preview at iteration 0 (:329-347): 128 x 128 at the first scale
+    assert prev.exists() and Image.open(prev).size == (128, 128)
+    assert sum(c[1] for c in fwd if c[-1] != "train") == 128 * 128
+    ck = torch.load(out / "saving_Parameters.tar", weights_only=False)
+    assert set(ck) >= {"saving_bm", "saving_uv", "saving_exp", "saving_pose", "saving_global_light", "iter"}
+    assert not torch.equal(ck["saving_global_light"].cpu(), torch.ones(2))          # the first Adam step moved it
+    assert ck["saving_bm"].shape[-1] == 50 and ck["saving_uv"].numel() == 256 and ck["saving_exp"].numel() == 30
