@@ -57,3 +57,28 @@ def test_reference_arm_prints_one_contract_line():
     assert d["value"] > 0 and d["e2e"]["value"] == d["value"]
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+
+
+def test_parity_stats_separates_opacity_gate_flips_from_arithmetic_error():
+    """bench.parity_stats: a ray whose sigma at the last sample changes sign between the two renderings is an opacity-gate
+    flip (the reference's relu(sigma) * 1e10 step, models/render_class.py:449) and is reported apart from the rest."""
+    import torch
+    g = torch.Generator().manual_seed(0)
+    ref = torch.rand(200, 3, generator=g)
+    got = ref + 1e-3 * torch.randn(200, 3, generator=g)
+    acc_ref = torch.ones(200)
+    acc = acc_ref.clone()
+    sig_ref = torch.randn(200, generator=g).abs() + 0.5          # firmly positive everywhere ...
+    sig = sig_ref.clone()
+    sig_ref[7], sig[7] = -2e-4, 3e-4                            # ... except one ray that sits on the step
+    got[7] += 0.6
+    acc[7] = 0.9
+    st = bench.parity_stats(got, acc, ref, acc_ref, sig, sig_ref)
+    assert st["opacity_gate_flips"] == 1 and st["gate_flips_with_visible_effect"] == 1
+    assert abs(st["gate_flip_max_abs_sigma_last_of_reference"] - 2e-4) < 1e-9
+    assert st["max_abs_rgb"] > 0.5 and st["max_abs_rgb_excluding_gate_flips"] < 1e-2
+    assert st["rays_over_3e-2"] == 1 and st["rays_over_3e-2_excluding_gate_flips"] == 0
+    assert st["psnr_db_excluding_gate_flips"] > st["psnr_db"] + 10
+    # without the sigmas a flip is a ray whose accumulated opacity differs by more than 0.5: this one (0.9 vs 1.0) is not
+    st2 = bench.parity_stats(got, acc, ref, acc_ref)
+    assert st2["opacity_gate_flips"] == 0 and "gate_flips_with_visible_effect" not in st2
