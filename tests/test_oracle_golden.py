@@ -124,3 +124,59 @@ def test_live_reference_crosscheck():
     b = O.raw2outputs(raw, z, d, None, False)
     for x, y in zip(a, b):
         assert_close_nan(y, x, 0.0)
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference tree not present on this box")
+def test_live_reference_crosscheck_more_functions():
+    """Fresh random inputs (not the fixtures' seeds) through the UNMODIFIED reference functions and the oracle's
+    restatements: sample_pdf (deterministic and seeded-random), the two embedders, get_rays, NeRF.forward through
+    run_network (latent expansion + concatenation orders), and a whole two-pass render_fitting call."""
+    ref = ref_loader.load()
+    g = torch.Generator().manual_seed(21)
+    # sample_pdf, tools/run_nerf_helpers.py:203-247 (det: u = linspace; pytest hook: np.random.seed(0) draws)
+    z = torch.sort(torch.rand(9, 40, generator=g) * 18 + 8, -1)[0]
+    bins = 0.5 * (z[:, 1:] + z[:, :-1])
+    w = torch.rand(9, 38, generator=g) ** 3
+    assert_close_nan(O.sample_pdf(bins, w, 24, det=True), ref.helpers.sample_pdf(bins, w, 24, det=True), 0.0)
+    np.random.seed(0)
+    u = torch.Tensor(np.random.rand(9, 24))
+    assert_close_nan(O.sample_pdf(bins, w, 24, det=False, u=u), ref.helpers.sample_pdf(bins, w, 24, det=False, pytest=True), 0.0)
+    # Embedder, models/model.py:15-63
+    x = torch.randn(33, 3, generator=g) * 9
+    for L in (10, 4):
+        fn, dim = ref.model.get_embedder(L, 0)
+        assert dim == O.embed_dim(L)
+        assert_close_nan(O.embed(x, L), fn(x), 0.0)
+    # get_rays, tools/run_nerf_helpers.py:153-168
+    K = np.array([[700.0, 0, 13.0], [0, 700.0, 9.5], [0, 0, 1]])
+    c2w = O.pose_spherical(-47.0, 12.0, 16.0)
+    for a, b in zip(O.get_rays(19, 26, K, c2w[:3, :4]), ref.helpers.get_rays(19, 26, K, c2w[:3, :4])):
+        assert_close_nan(a, b, 0.0)
+    # run_network + NeRF.forward (models/render_class.py:69-109, models/model.py:121-137) and a full render_fitting call
+    coarse, fine, renderer = ref_loader.build_reference(31, 256, 8, 256, 8)
+    oc, of, ostyle = O.build_nets(31, 256, 8, 256, 8)
+    shape = torch.randn(1, 50, generator=g) * 0.05
+    tex = torch.randn(256, generator=g) * 0.3
+    exp = torch.rand(1, 30, generator=g)
+    ro, rd = O.get_rays(5, 7, K, c2w[:3, :4])
+    ro, rd = ro.reshape(-1, 3), rd.reshape(-1, 3)
+    # (one chunk, as in the oracle: with chunk=16 the reference's own `raw` moves by 0.2 at a few zero-weight samples —
+    #  different GEMM shapes round the coarse weights differently and inverse-CDF resampling is discontinuous — while the
+    #  rendered maps still agree to 1e-4)
+    with torch.no_grad():
+        out = renderer.render_fitting(5, 7, K, chunk=64, rays=(ro, rd), shapeCodes=shape, uvCodes=tex, expType=20, expCodes=exp,
+                                      network_fn=coarse, network_fine=fine, N_samples=24, N_importance=16, perturb=0.0,
+                                      raw_noise_std=0.0, white_bkgd=True, lindisp=False, use_viewdirs=True, ndc=False,
+                                      near=8.0, far=26.0, retraw=True)
+        em = O.expression_mod(ostyle, shape, exp)
+        mine = O.render_rays(O.make_ray_batch(ro, rd, 8.0, 26.0), oc, of, shape, em, tex, N_samples=24, N_importance=16,
+                             white_bkgd=True, retraw=True)
+        # network query at explicit points: the renderer's run_network is the reference's network_query_fn
+        pts = torch.randn(11, 6, 3, generator=g) * 4
+        vd = torch.nn.functional.normalize(torch.randn(11, 3, generator=g), dim=-1)
+        raw_ref = renderer.run_network(pts, vd, fn=fine)
+        raw_mine = O.run_network(pts, vd, of, shape, em, tex)
+    assert_close_nan(raw_mine, raw_ref, 2e-5, 1e-5, what="run_network")
+    for k, v in (("rgb_map", out[0]), ("disp_map", out[1]), ("acc_map", out[2]), ("rgb0", out[3]["rgb0"]),
+                 ("acc0", out[3]["acc0"]), ("z_std", out[3]["z_std"]), ("raw", out[3]["raw"])):
+        assert_close_nan(mine[k], v, 1e-4, 1e-4, what=f"live render_fitting:{k}")
