@@ -296,6 +296,13 @@ def parity_vs_oracle(renderer, keep, kw, dev):
                                                                last(ref["raw"]))
     if "rgb0" in extras and "rgb0" in ref:
         out["max_abs_rgb0"] = float((extras["rgb0"].reshape(-1, 3) - ref["rgb0"].reshape(-1, 3)).abs().max().item())
+    # the metric's "PSNR delta vs reference" in one number: PSNR(engine, fp32 reference) minus PSNR(reference in its TF32
+    # mode, fp32 reference), over all rays and over the rays that are not opacity-gate flips (positive = engine closer)
+    e, t = out["engine_vs_reference_fp32"], out.get("reference_tf32_vs_reference_fp32")
+    if t is not None:
+        out["psnr_delta_db_vs_reference_tf32_mode"] = {
+            "all_rays": e["psnr_db"] - t["psnr_db"],
+            "excluding_gate_flips": e["psnr_db_excluding_gate_flips"] - t["psnr_db_excluding_gate_flips"]}
     return out
 
 
